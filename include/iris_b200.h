@@ -1,0 +1,139 @@
+/*
+ * iris_b200.h -- C ABI of the B200-native matching backend for recmo/mpc-iris-code.
+ *
+ * This is the boundary a `src/arch/cuda.rs` backend would bind (see INTEGRATION.md for the
+ * Rust `extern "C"` block).  It replaces, for the matching hot path only,
+ *
+ *   arch::dot_u16 / arch::dot_bool              src/arch/mod.rs:5, src/arch/generic.rs:4-16
+ *   DistanceEngine::{new, batch_process}        src/lib.rs:28-52
+ *   MasksEngine::{new, batch_process}           src/lib.rs:55-79
+ *   distances / denominators                    src/lib.rs:82-94
+ *
+ * keeping the reference's byte layouts at the boundary:
+ *
+ *   EncodedBits = [u16; 12800]   25 600 B   src/encoded_bits.rs:13-15   (k = row*200 + col)
+ *   Bits        = [u64; 200]      1 600 B   src/bits.rs:13-15           (bit k = byte k/8, bit k%8)
+ *   Template    = {pattern, mask} 3 200 B   src/template.rs:11-29
+ *   result row  = [u16; 31]          62 B   src/lib.rs:42, slot j <-> rotation j-15, rows packed
+ *
+ * All functions return IRIS_OK (0) or a negative iris_status; iris_last_error() gives the
+ * message of the calling thread's last failure.  Nothing aborts or unwinds across the ABI:
+ * the reference's `assert_eq!(out.len(), db.len())` panic (src/lib.rs:43,70) becomes
+ * IRIS_ERR_INVALID.  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with IRIS_ERR_CUDA.
+ *
+ * Threading: calls on one handle (database or engine) must be serialised by the caller
+ * (the reference calls batch_process from one spawn_blocking thread at a time,
+ * src/main.rs:425-431, 510-516); distinct handles may be used from distinct threads.
+ * Ownership: the library owns device memory behind the opaque handles; the caller owns
+ * every buffer it passes in, and no pointer is retained after a call returns.
+ */
+#ifndef IRIS_B200_H
+#define IRIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRIS_COLS 200      /* src/lib.rs:10 */
+#define IRIS_ROWS 64       /* src/lib.rs:11 */
+#define IRIS_BITS 12800    /* src/lib.rs:12 */
+#define IRIS_LIMBS 200     /* src/bits.rs:10 */
+#define IRIS_ROTATIONS 31  /* src/lib.rs:34-35: -15..=15 */
+
+typedef enum iris_status {
+    IRIS_OK = 0,
+    IRIS_ERR_INVALID = -1, /* bad argument / length mismatch (reference: assert_eq! panic) */
+    IRIS_ERR_CUDA = -2,    /* CUDA runtime or kernel failure, or no device */
+    IRIS_ERR_NOMEM = -3,   /* host or device allocation failed */
+    IRIS_ERR_STATE = -4    /* handle does not hold what the call needs (e.g. no masks loaded) */
+} iris_status;
+
+typedef struct iris_db iris_db;                           /* HBM-resident database shard */
+typedef struct iris_distance_engine iris_distance_engine; /* DistanceEngine  (src/lib.rs:28-31) */
+typedef struct iris_masks_engine iris_masks_engine;       /* MasksEngine     (src/lib.rs:55-58) */
+
+const char *iris_last_error(void);
+int iris_device_count(int *count);
+/* Kernels launched by the library since it was loaded (benchmark bookkeeping). */
+uint64_t iris_launch_count(void);
+
+/* ---- per-pair arch entry points: src/arch/generic.rs:11-16 and :4-9 (host pointers).  API
+ * parity only -- one launch per pair cannot amortise; use the engines for throughput. ---- */
+int iris_dot_u16(int device, const uint16_t a[IRIS_BITS], const uint16_t b[IRIS_BITS], uint16_t *out);
+int iris_dot_bool(int device, const uint64_t a[IRIS_LIMBS], const uint64_t b[IRIS_LIMBS], uint16_t *out);
+
+/* ---- database shard: what the reference mmaps as &[EncodedBits] (src/main.rs:389-391) and
+ * &[Bits] (src/main.rs:458-461), loaded ONCE into HBM and re-tiled for the tensor pipeline. ---- */
+#define IRIS_DB_SHARES 1u
+#define IRIS_DB_MASKS 2u
+int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags, iris_db **out);
+int iris_db_destroy(iris_db *db);
+int iris_db_clear(iris_db *db); /* forget all rows, keep the allocation */
+int iris_db_len(const iris_db *db, uint64_t *n_shares, uint64_t *n_masks);
+/* Append rows given in the reference's flat-file layouts (host pointers). */
+int iris_db_append_shares(iris_db *db, const uint16_t *rows /* [n][12800] */, uint64_t n);
+int iris_db_append_masks(iris_db *db, const uint64_t *rows /* [n][200] */, uint64_t n);
+/* Append n synthetic rows (uniform u16 shares and/or uniform mask bits, per `flags` of the
+ * shard) produced on the device by a counter-based generator keyed by (seed, row id);
+ * row ids are first_row_id, first_row_id+1, ...  (oracle/iris_oracle.c restates the generator). */
+int iris_db_generate(iris_db *db, uint64_t seed, uint64_t first_row_id, uint64_t n);
+/* Read rows back in the reference layouts (inverse of the loader; tests and debugging). */
+int iris_db_read_shares(iris_db *db, uint64_t row_begin, uint64_t n, uint16_t *out /* [n][12800] */);
+int iris_db_read_masks(iris_db *db, uint64_t row_begin, uint64_t n, uint64_t *out /* [n][200] */);
+/* Run all work of this shard on the given cudaStream_t (NULL = the library's own stream). */
+int iris_db_set_stream(iris_db *db, void *cuda_stream);
+int iris_db_synchronize(iris_db *db);
+
+/* ---- DistanceEngine (src/lib.rs:28-52) ---- */
+/* new: prepares the 31 rotations (-15..=15) of `query` as the tensor-core operand image. */
+int iris_distance_engine_new(int device, const uint16_t query[IRIS_BITS], iris_distance_engine **out);
+int iris_distance_engine_free(iris_distance_engine *e);
+/* batch_process(&self, out, db) with the reference's exact shape: `db` is a HOST slice of
+ * db_len EncodedBits, `out` a HOST slice of out_len [u16;31]; out_len != db_len is an error.
+ * Rows are streamed to the GPU, so this call is PCIe-bound; it exists for drop-in parity. */
+int iris_distance_engine_batch_process(iris_distance_engine *e, uint16_t *out, uint64_t out_len,
+                                       const uint16_t *db, uint64_t db_len);
+/* batch_process against rows [row_begin,row_end) of an HBM-resident shard -- the production
+ * path (the reference calls batch_process on 20 000-row chunks of its mmap, src/main.rs:428).
+ * `out` ([row_end-row_begin][31]) may be host memory (pageable or pinned) or device memory. */
+int iris_distance_engine_batch_process_resident(iris_distance_engine *e, uint16_t *out, uint64_t out_len,
+                                                iris_db *db, uint64_t row_begin, uint64_t row_end);
+
+/* ---- MasksEngine (src/lib.rs:55-79) ---- */
+int iris_masks_engine_new(int device, const uint64_t query_mask[IRIS_LIMBS], iris_masks_engine **out);
+int iris_masks_engine_free(iris_masks_engine *e);
+int iris_masks_engine_batch_process(iris_masks_engine *e, uint16_t *out, uint64_t out_len, const uint64_t *db,
+                                    uint64_t db_len);
+int iris_masks_engine_batch_process_resident(iris_masks_engine *e, uint16_t *out, uint64_t out_len, iris_db *db,
+                                             uint64_t row_begin, uint64_t row_end);
+
+/* ---- fused scan: both engines over the same rows in ONE pass over HBM (shares + masks read
+ * once; BASELINE config 2).  Either engine/out pair may be NULL. ---- */
+int iris_match_resident(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
+                        uint64_t row_end, uint16_t *distances_out, uint16_t *denominators_out);
+
+/* ---- single-pair wrappers: src/lib.rs:82-87 and :89-94 ---- */
+int iris_distances(int device, const uint16_t query[IRIS_BITS], const uint16_t entry[IRIS_BITS],
+                   uint16_t out[IRIS_ROTATIONS]);
+int iris_denominators(int device, const uint64_t query[IRIS_LIMBS], const uint64_t entry[IRIS_LIMBS],
+                      uint16_t out[IRIS_ROTATIONS]);
+
+/* ---- verification helpers (CUDA-core kernels over the same HBM image; NOT the product path):
+ * used by the GPU tests to cross-check the tensor-core scan at full database size. ---- */
+int iris_check_distances_simt(iris_db *db, const uint16_t query[IRIS_BITS], uint64_t row_begin, uint64_t row_end,
+                              uint16_t *out);
+int iris_check_denominators_simt(iris_db *db, const uint64_t query_mask[IRIS_LIMBS], uint64_t row_begin,
+                                 uint64_t row_end, uint16_t *out);
+/* Debug: run the fused scan over [row_begin,row_end) (row_begin multiple of 128) and dump the raw s32
+ * accumulators, [tiles*128][128] = {S00[32], S10[32], S01[32], 128*popcount[32]} per row, to host. */
+int iris_debug_raw_accumulators(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
+                                uint64_t row_end, int32_t *raw_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRIS_B200_H */

@@ -1,0 +1,29 @@
+"""B200-native matching backend for recmo/mpc-iris-code (distances + denominators hot path).
+
+Host-side mirror of the reference's engine API (src/lib.rs:28-94) over the C ABI in
+include/iris_b200.h.  The directory is named after the reference (`mpc-iris-code_b200/`);
+import it as `mpc_iris_code_b200` (a shim package at the repo root extends its path here).
+
+There is no CPU fallback: every compute call goes through libiris_b200.so and fails loudly
+(IrisError / OSError) if the library or a CUDA device is missing.
+"""
+from .api import (  # noqa: F401
+    BITS,
+    COLS,
+    LIMBS,
+    ROTATIONS,
+    ROWS,
+    Database,
+    DistanceEngine,
+    IrisError,
+    MasksEngine,
+    denominators,
+    device_count,
+    distances,
+    dot_bool,
+    dot_u16,
+    launch_count,
+    lib,
+    library_path,
+    match,
+)

@@ -1,0 +1,356 @@
+"""ctypes binding of include/iris_b200.h, shaped like the reference's Rust API.
+
+Reference names kept: DistanceEngine / MasksEngine with new (constructor) and batch_process,
+distances(), denominators(), dot_u16(), dot_bool()  (src/lib.rs:28-94, src/arch/mod.rs:5).
+Buffers are numpy arrays (host) or torch CUDA tensors (device); layouts are the reference's
+(EncodedBits = u16[12800], Bits = u64[200], result rows = u16[31]).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+COLS = 200          # src/lib.rs:10
+ROWS = 64           # src/lib.rs:11
+BITS = ROWS * COLS  # src/lib.rs:12
+LIMBS = BITS // 64  # src/bits.rs:10
+ROTATIONS = 31      # src/lib.rs:34-35
+
+IRIS_DB_SHARES = 1
+IRIS_DB_MASKS = 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class IrisError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"iris_b200 error {code}: {message}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "libiris_b200.so")
+
+
+def lib():
+    """Loads libiris_b200.so (building it with nvcc if it is absent).  No fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        from . import build as _build
+
+        _build.build()
+    L = ctypes.CDLL(path)
+    vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    sigs = {
+        "iris_device_count": [ctypes.POINTER(i32)],
+        "iris_dot_u16": [i32, vp, vp, vp],
+        "iris_dot_bool": [i32, vp, vp, vp],
+        "iris_db_create": [i32, u64, u32, pp],
+        "iris_db_destroy": [vp],
+        "iris_db_clear": [vp],
+        "iris_db_len": [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)],
+        "iris_db_append_shares": [vp, vp, u64],
+        "iris_db_append_masks": [vp, vp, u64],
+        "iris_db_generate": [vp, u64, u64, u64],
+        "iris_db_read_shares": [vp, u64, u64, vp],
+        "iris_db_read_masks": [vp, u64, u64, vp],
+        "iris_db_set_stream": [vp, vp],
+        "iris_db_synchronize": [vp],
+        "iris_distance_engine_new": [i32, vp, pp],
+        "iris_distance_engine_free": [vp],
+        "iris_distance_engine_batch_process": [vp, vp, u64, vp, u64],
+        "iris_distance_engine_batch_process_resident": [vp, vp, u64, vp, u64, u64],
+        "iris_masks_engine_new": [i32, vp, pp],
+        "iris_masks_engine_free": [vp],
+        "iris_masks_engine_batch_process": [vp, vp, u64, vp, u64],
+        "iris_masks_engine_batch_process_resident": [vp, vp, u64, vp, u64, u64],
+        "iris_match_resident": [vp, vp, vp, u64, u64, vp, vp],
+        "iris_distances": [i32, vp, vp, vp],
+        "iris_denominators": [i32, vp, vp, vp],
+        "iris_check_distances_simt": [vp, vp, u64, u64, vp],
+        "iris_check_denominators_simt": [vp, vp, u64, u64, vp],
+        "iris_debug_raw_accumulators": [vp, vp, vp, u64, u64, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = i32
+    L.iris_last_error.restype = ctypes.c_char_p
+    L.iris_last_error.argtypes = []
+    L.iris_launch_count.restype = u64
+    L.iris_launch_count.argtypes = []
+    _LIB = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise IrisError(rc, lib().iris_last_error().decode(errors="replace"))
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x, dtype, min_elems: int, what: str) -> int:
+    """Raw address of a numpy array (host) or torch tensor (host or CUDA) after layout checks."""
+    if x is None:
+        return 0
+    if _is_torch(x):
+        import torch
+
+        want = {np.uint16: (torch.uint16, torch.int16), np.uint64: (torch.uint64, torch.int64), np.int32: (torch.int32,)}[dtype]
+        if x.dtype not in want:
+            raise TypeError(f"{what}: expected torch dtype in {want}, got {x.dtype}")
+        if not x.is_contiguous():
+            raise ValueError(f"{what}: tensor must be contiguous")
+        if x.numel() < min_elems:
+            raise ValueError(f"{what}: needs {min_elems} elements, has {x.numel()}")
+        return x.data_ptr()
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{what}: expected numpy array or torch tensor, got {type(x)}")
+    if x.dtype != dtype:
+        raise TypeError(f"{what}: expected dtype {np.dtype(dtype)}, got {x.dtype}")
+    if not x.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"{what}: array must be C-contiguous")
+    if x.size < min_elems:
+        raise ValueError(f"{what}: needs {min_elems} elements, has {x.size}")
+    return x.ctypes.data
+
+
+def _numel(x) -> int:
+    return x.numel() if _is_torch(x) else x.size
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    _check(lib().iris_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def launch_count() -> int:
+    return int(lib().iris_launch_count())
+
+
+# ------------------------------------------------------------------ arch entry points
+def dot_u16(a, b, device: int = 0) -> int:
+    """arch::dot_u16 (src/arch/generic.rs:11-16)."""
+    out = np.zeros(1, np.uint16)
+    _check(lib().iris_dot_u16(device, _ptr(a, np.uint16, BITS, "a"), _ptr(b, np.uint16, BITS, "b"), out.ctypes.data))
+    return int(out[0])
+
+
+def dot_bool(a, b, device: int = 0) -> int:
+    """arch::dot_bool (src/arch/generic.rs:4-9)."""
+    out = np.zeros(1, np.uint16)
+    _check(lib().iris_dot_bool(device, _ptr(a, np.uint64, LIMBS, "a"), _ptr(b, np.uint64, LIMBS, "b"), out.ctypes.data))
+    return int(out[0])
+
+
+# ------------------------------------------------------------------ database shard
+class Database:
+    """HBM-resident shard: the reference's mmapped &[EncodedBits] / &[Bits] (src/main.rs:389-391, 458-461)."""
+
+    def __init__(self, capacity_rows: int, device: int = 0, shares: bool = True, masks: bool = True):
+        self._h = ctypes.c_void_p()
+        self.device = device
+        flags = (IRIS_DB_SHARES if shares else 0) | (IRIS_DB_MASKS if masks else 0)
+        _check(lib().iris_db_create(device, capacity_rows, flags, ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().iris_db_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _lens(self):
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        _check(lib().iris_db_len(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    @property
+    def len_shares(self) -> int:
+        return self._lens()[0]
+
+    @property
+    def len_masks(self) -> int:
+        return self._lens()[1]
+
+    def clear(self) -> None:
+        _check(lib().iris_db_clear(self._h))
+
+    def append_shares(self, rows) -> None:
+        n = _numel(rows) // BITS
+        if n * BITS != _numel(rows):
+            raise ValueError("shares must be [n][12800] u16")
+        _check(lib().iris_db_append_shares(self._h, _ptr(rows, np.uint16, n * BITS, "rows"), n))
+
+    def append_masks(self, rows) -> None:
+        n = _numel(rows) // LIMBS
+        if n * LIMBS != _numel(rows):
+            raise ValueError("masks must be [n][200] u64")
+        _check(lib().iris_db_append_masks(self._h, _ptr(rows, np.uint64, n * LIMBS, "rows"), n))
+
+    def generate(self, seed: int, first_row_id: int, n: int) -> None:
+        _check(lib().iris_db_generate(self._h, seed, first_row_id, n))
+
+    def read_shares(self, row_begin: int, n: int) -> np.ndarray:
+        out = np.empty((n, BITS), np.uint16)
+        _check(lib().iris_db_read_shares(self._h, row_begin, n, out.ctypes.data))
+        return out
+
+    def read_masks(self, row_begin: int, n: int) -> np.ndarray:
+        out = np.empty((n, LIMBS), np.uint64)
+        _check(lib().iris_db_read_masks(self._h, row_begin, n, out.ctypes.data))
+        return out
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        _check(lib().iris_db_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self) -> None:
+        _check(lib().iris_db_synchronize(self._h))
+
+    # verification helpers (CUDA-core kernels, not the product path)
+    def check_distances_simt(self, query, row_begin: int, row_end: int, out=None):
+        if out is None:
+            out = np.empty((row_end - row_begin, ROTATIONS), np.uint16)
+        _check(lib().iris_check_distances_simt(self._h, _ptr(query, np.uint16, BITS, "query"), row_begin, row_end,
+                                               _ptr(out, np.uint16, (row_end - row_begin) * ROTATIONS, "out")))
+        return out
+
+    def check_denominators_simt(self, qmask, row_begin: int, row_end: int, out=None):
+        if out is None:
+            out = np.empty((row_end - row_begin, ROTATIONS), np.uint16)
+        _check(lib().iris_check_denominators_simt(self._h, _ptr(qmask, np.uint64, LIMBS, "qmask"), row_begin, row_end,
+                                                  _ptr(out, np.uint16, (row_end - row_begin) * ROTATIONS, "out")))
+        return out
+
+
+def _out_len(out) -> int:
+    n = _numel(out)
+    if n % ROTATIONS:
+        raise ValueError("out must be [n][31] u16")
+    return n // ROTATIONS
+
+
+# ------------------------------------------------------------------ engines
+class DistanceEngine:
+    """DistanceEngine (src/lib.rs:28-52): new(query) prepares rotations -15..=15; batch_process fills out[i][j]."""
+
+    def __init__(self, query, device: int = 0):
+        self._h = ctypes.c_void_p()
+        self.device = device
+        _check(lib().iris_distance_engine_new(device, _ptr(query, np.uint16, BITS, "query"), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().iris_distance_engine_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def batch_process(self, out, db, row_begin: Optional[int] = None, row_end: Optional[int] = None) -> None:
+        """batch_process(&self, out, db).  `db` is either a host array of EncodedBits ([n][12800] u16,
+        the reference's literal signature) or a resident Database (optionally a row range of it)."""
+        if isinstance(db, Database):
+            rb = 0 if row_begin is None else row_begin
+            re = db.len_shares if row_end is None else row_end
+            _check(lib().iris_distance_engine_batch_process_resident(
+                self._h, _ptr(out, np.uint16, 0, "out"), _out_len(out), db._h, rb, re))
+        else:
+            n = _numel(db) // BITS
+            if n * BITS != _numel(db):
+                raise ValueError("db must be [n][12800] u16")
+            _check(lib().iris_distance_engine_batch_process(
+                self._h, _ptr(out, np.uint16, 0, "out"), _out_len(out), _ptr(db, np.uint16, 0, "db"), n))
+
+
+class MasksEngine:
+    """MasksEngine (src/lib.rs:55-79)."""
+
+    def __init__(self, query_mask, device: int = 0):
+        self._h = ctypes.c_void_p()
+        self.device = device
+        _check(lib().iris_masks_engine_new(device, _ptr(query_mask, np.uint64, LIMBS, "query_mask"), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().iris_masks_engine_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def batch_process(self, out, db, row_begin: Optional[int] = None, row_end: Optional[int] = None) -> None:
+        if isinstance(db, Database):
+            rb = 0 if row_begin is None else row_begin
+            re = db.len_masks if row_end is None else row_end
+            _check(lib().iris_masks_engine_batch_process_resident(
+                self._h, _ptr(out, np.uint16, 0, "out"), _out_len(out), db._h, rb, re))
+        else:
+            n = _numel(db) // LIMBS
+            if n * LIMBS != _numel(db):
+                raise ValueError("db must be [n][200] u64")
+            _check(lib().iris_masks_engine_batch_process(
+                self._h, _ptr(out, np.uint16, 0, "out"), _out_len(out), _ptr(db, np.uint64, 0, "db"), n))
+
+
+def match(distance_engine: Optional[DistanceEngine], masks_engine: Optional[MasksEngine], db: Database,
+          row_begin: int, row_end: int, distances_out=None, denominators_out=None) -> None:
+    """Fused scan: both engines over rows [row_begin,row_end) in one pass over HBM."""
+    n = (row_end - row_begin) * ROTATIONS
+    _check(lib().iris_match_resident(
+        distance_engine._h if distance_engine else None,
+        masks_engine._h if masks_engine else None,
+        db._h, row_begin, row_end,
+        _ptr(distances_out, np.uint16, n, "distances_out") if distance_engine else None,
+        _ptr(denominators_out, np.uint16, n, "denominators_out") if masks_engine else None))
+
+
+def raw_accumulators(distance_engine, masks_engine, db: Database, row_begin: int, row_end: int) -> np.ndarray:
+    tiles = (row_end - row_begin + 127) // 128
+    raw = np.empty((tiles * 128, 128), np.int32)
+    _check(lib().iris_debug_raw_accumulators(
+        distance_engine._h if distance_engine else None, masks_engine._h if masks_engine else None,
+        db._h, row_begin, row_end, raw.ctypes.data))
+    return raw
+
+
+def distances(query, entry, device: int = 0) -> np.ndarray:
+    """distances(query, entry) -> [u16;31]  (src/lib.rs:82-87)."""
+    out = np.zeros(ROTATIONS, np.uint16)
+    _check(lib().iris_distances(device, _ptr(query, np.uint16, BITS, "query"), _ptr(entry, np.uint16, BITS, "entry"), out.ctypes.data))
+    return out
+
+
+def denominators(query, entry, device: int = 0) -> np.ndarray:
+    """denominators(query, entry) -> [u16;31]  (src/lib.rs:89-94)."""
+    out = np.zeros(ROTATIONS, np.uint16)
+    _check(lib().iris_denominators(device, _ptr(query, np.uint64, LIMBS, "query"), _ptr(entry, np.uint64, LIMBS, "entry"), out.ctypes.data))
+    return out

@@ -1,0 +1,749 @@
+// Host runtime behind include/iris_b200.h: handles, loader, stream pipeline, error channel.
+// Mirrors the reference's engine API (src/lib.rs:28-94); see the header for the mapping.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/iris_b200.h"
+#include "iris_kernels.cuh"
+
+using namespace iris;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? IRIS_ERR_NOMEM : IRIS_ERR_CUDA, "%s failed: %s", #expr, \
+                        cudaGetErrorString(e_));                                                     \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+extern "C" const char* iris_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int iris_device_count(int* count) {
+    if (!count) return fail(IRIS_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(IRIS_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return IRIS_OK;
+}
+
+extern "C" uint64_t iris_launch_count(void) { return launch_count(); }
+
+// ------------------------------------------------------------------------------------ handles
+static constexpr uint64_t kStageRows = 2048;                      // loader staging: 52 MB of shares
+static constexpr uint64_t kResultChunkTilesPerSm = 8;             // host-output pipeline granularity
+
+struct iris_db {
+    int device = 0;
+    int num_sms = 148;
+    uint64_t capacity = 0;   // rows, multiple of 128
+    uint32_t flags = 0;
+    uint64_t n_shares = 0, n_masks = 0;
+    uint8_t* d_shares = nullptr;
+    uint8_t* d_masks = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    void* d_stage = nullptr;         // loader staging (reference-layout rows)
+    uint16_t* d_res[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][dist|den]
+    uint64_t res_rows = 0;
+    int* d_error = nullptr;
+};
+
+struct iris_distance_engine {
+    int device = 0;
+    uint16_t* d_query = nullptr;
+    uint8_t* d_qd = nullptr;
+    iris_db* scratch = nullptr;      // for the host-slice batch_process
+};
+
+struct iris_masks_engine {
+    int device = 0;
+    uint8_t* d_qmask = nullptr;
+    uint8_t* d_qm = nullptr;
+    iris_db* scratch = nullptr;
+};
+
+// small free-list so that engine construction per query does not hit cudaMalloc every time
+struct BufPool {
+    std::mutex mu;
+    std::vector<std::pair<int, void*>> qd, qm, q16, q8;
+    void* take(std::vector<std::pair<int, void*>>& v, int dev) {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].first == dev) {
+                void* p = v[i].second;
+                v.erase(v.begin() + i);
+                return p;
+            }
+        return nullptr;
+    }
+    void give(std::vector<std::pair<int, void*>>& v, int dev, void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (v.size() < 64) {
+            v.emplace_back(dev, p);
+            return;
+        }
+        cudaFree(p);
+    }
+};
+static BufPool g_pool;
+
+static int pooled_alloc(std::vector<std::pair<int, void*>>& v, int dev, size_t bytes, void** out) {
+    void* p = g_pool.take(v, dev);
+    if (!p) CK(cudaMalloc(&p, bytes));
+    *out = p;
+    return IRIS_OK;
+}
+
+// ------------------------------------------------------------------------------------ database
+extern "C" int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags, iris_db** out) {
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!(flags & (IRIS_DB_SHARES | IRIS_DB_MASKS)) || (flags & ~(IRIS_DB_SHARES | IRIS_DB_MASKS)))
+        return fail(IRIS_ERR_INVALID, "flags must be a combination of IRIS_DB_SHARES and IRIS_DB_MASKS");
+    if (capacity_rows == 0) return fail(IRIS_ERR_INVALID, "capacity_rows must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(IRIS_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(IRIS_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(IRIS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    iris_db* db = new (std::nothrow) iris_db();
+    if (!db) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+    db->device = device;
+    db->flags = flags;
+    db->capacity = (capacity_rows + kTileRows - 1) / kTileRows * kTileRows;
+    const uint64_t tiles = db->capacity / kTileRows;
+    int rc = IRIS_OK;
+    auto body = [&]() -> int {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) return fail(IRIS_ERR_CUDA, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+        db->num_sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&db->own_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
+        db->stream = db->own_stream;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&db->ev_scan[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&db->ev_copy[i], cudaEventDisableTiming));
+        }
+        CK(cudaMalloc(&db->d_error, sizeof(int)));
+        CK(cudaMemset(db->d_error, 0, sizeof(int)));
+        if (flags & IRIS_DB_SHARES) {
+            CK(cudaMalloc(&db->d_shares, tiles * kShareTileBytes));
+            CK(cudaMemsetAsync(db->d_shares, 0, tiles * kShareTileBytes, db->stream));
+        }
+        if (flags & IRIS_DB_MASKS) {
+            CK(cudaMalloc(&db->d_masks, tiles * kMaskTileBytes));
+            CK(cudaMemsetAsync(db->d_masks, 0, tiles * kMaskTileBytes, db->stream));
+        }
+        CK(cudaStreamSynchronize(db->stream));
+        return IRIS_OK;
+    };
+    rc = body();
+    if (rc != IRIS_OK) {
+        std::string keep = g_last_error;
+        iris_db_destroy(db);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = db;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_destroy(iris_db* db) {
+    if (!db) return IRIS_OK;
+    DeviceGuard g(db->device);
+    if (db->own_stream) cudaStreamSynchronize(db->own_stream);
+    if (db->copy_stream) cudaStreamSynchronize(db->copy_stream);
+    cudaFree(db->d_shares);
+    cudaFree(db->d_masks);
+    cudaFree(db->d_stage);
+    cudaFree(db->d_error);
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 2; ++k) cudaFree(db->d_res[b][k]);
+    for (int i = 0; i < 2; ++i) {
+        if (db->ev_scan[i]) cudaEventDestroy(db->ev_scan[i]);
+        if (db->ev_copy[i]) cudaEventDestroy(db->ev_copy[i]);
+    }
+    if (db->own_stream) cudaStreamDestroy(db->own_stream);
+    if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
+    cudaGetLastError();
+    delete db;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_clear(iris_db* db) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    db->n_shares = db->n_masks = 0;   // stale rows beyond n_* are never stored by a scan
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_len(const iris_db* db, uint64_t* n_shares, uint64_t* n_masks) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    if (n_shares) *n_shares = db->n_shares;
+    if (n_masks) *n_masks = db->n_masks;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_set_stream(iris_db* db, void* cuda_stream) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    DeviceGuard g(db->device);
+    CK(cudaStreamSynchronize(db->stream));
+    db->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : db->own_stream;
+    return IRIS_OK;
+}
+
+static int check_error_flag(iris_db* db) {
+    int h = 0;
+    CK(cudaMemcpy(&h, db->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h != 0) return fail(IRIS_ERR_CUDA, "scan kernel watchdog fired (code %d)", h);
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_synchronize(iris_db* db) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    DeviceGuard g(db->device);
+    CK(cudaStreamSynchronize(db->stream));
+    CK(cudaStreamSynchronize(db->copy_stream));
+    return check_error_flag(db);
+}
+
+static int ensure_stage(iris_db* db) {
+    if (!db->d_stage) CK(cudaMalloc(&db->d_stage, kStageRows * IRIS_BITS * sizeof(uint16_t)));
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_append_shares(iris_db* db, const uint16_t* rows, uint64_t n) {
+    if (!db || (!rows && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_SHARES)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_SHARES");
+    if (db->n_shares + n > db->capacity)
+        return fail(IRIS_ERR_INVALID, "append of %llu rows exceeds capacity %llu", (unsigned long long)n, (unsigned long long)db->capacity);
+    DeviceGuard g(db->device);
+    if (is_device_pointer(rows)) {
+        CK(launch_retile_shares(rows, n, db->d_shares, db->n_shares, db->stream));
+    } else {
+        int rc = ensure_stage(db);
+        if (rc) return rc;
+        for (uint64_t off = 0; off < n; off += kStageRows) {
+            const uint64_t m = std::min(kStageRows, n - off);
+            CK(cudaMemcpyAsync(db->d_stage, rows + off * IRIS_BITS, m * IRIS_BITS * sizeof(uint16_t), cudaMemcpyHostToDevice, db->stream));
+            CK(launch_retile_shares(static_cast<const uint16_t*>(db->d_stage), m, db->d_shares, db->n_shares + off, db->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(db->stream));
+    db->n_shares += n;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_append_masks(iris_db* db, const uint64_t* rows, uint64_t n) {
+    if (!db || (!rows && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_MASKS)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_MASKS");
+    if (db->n_masks + n > db->capacity)
+        return fail(IRIS_ERR_INVALID, "append of %llu rows exceeds capacity %llu", (unsigned long long)n, (unsigned long long)db->capacity);
+    DeviceGuard g(db->device);
+    if (is_device_pointer(rows)) {
+        CK(launch_retile_masks(reinterpret_cast<const uint8_t*>(rows), n, db->d_masks, db->n_masks, db->stream));
+    } else {
+        int rc = ensure_stage(db);
+        if (rc) return rc;
+        const uint64_t step = kStageRows * 16;   // same staging buffer, 1600-byte rows
+        for (uint64_t off = 0; off < n; off += step) {
+            const uint64_t m = std::min(step, n - off);
+            CK(cudaMemcpyAsync(db->d_stage, rows + off * IRIS_LIMBS, m * IRIS_MASK_BYTES, cudaMemcpyHostToDevice, db->stream));
+            CK(launch_retile_masks(static_cast<const uint8_t*>(db->d_stage), m, db->d_masks, db->n_masks + off, db->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(db->stream));
+    db->n_masks += n;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_generate(iris_db* db, uint64_t seed, uint64_t first_row_id, uint64_t n) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    const bool s = db->flags & IRIS_DB_SHARES, m = db->flags & IRIS_DB_MASKS;
+    if (s && m && db->n_shares != db->n_masks) return fail(IRIS_ERR_STATE, "shares and masks lengths differ");
+    const uint64_t row0 = s ? db->n_shares : db->n_masks;
+    if (row0 + n > db->capacity) return fail(IRIS_ERR_INVALID, "generate exceeds capacity");
+    DeviceGuard g(db->device);
+    // bounded launches (grid dimension limits)
+    const uint64_t step = 1u << 18;
+    for (uint64_t off = 0; off < n; off += step) {
+        const uint64_t cnt = std::min(step, n - off);
+        CK(launch_generate(s ? db->d_shares : nullptr, m ? db->d_masks : nullptr, seed, first_row_id + off, row0 + off, cnt, db->stream));
+    }
+    CK(cudaStreamSynchronize(db->stream));
+    if (s) db->n_shares += n;
+    if (m) db->n_masks += n;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_read_shares(iris_db* db, uint64_t row_begin, uint64_t n, uint16_t* out) {
+    if (!db || (!out && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_SHARES)) return fail(IRIS_ERR_STATE, "no shares in this shard");
+    if (row_begin + n > db->n_shares) return fail(IRIS_ERR_INVALID, "row range beyond loaded shares");
+    DeviceGuard g(db->device);
+    int rc = ensure_stage(db);
+    if (rc) return rc;
+    for (uint64_t off = 0; off < n; off += kStageRows) {
+        const uint64_t m = std::min(kStageRows, n - off);
+        CK(launch_untile_shares(db->d_shares, row_begin + off, m, static_cast<uint16_t*>(db->d_stage), db->stream));
+        CK(cudaMemcpyAsync(out + off * IRIS_BITS, db->d_stage, m * IRIS_BITS * sizeof(uint16_t), cudaMemcpyDeviceToHost, db->stream));
+        CK(cudaStreamSynchronize(db->stream));
+    }
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_read_masks(iris_db* db, uint64_t row_begin, uint64_t n, uint64_t* out) {
+    if (!db || (!out && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_MASKS)) return fail(IRIS_ERR_STATE, "no masks in this shard");
+    if (row_begin + n > db->n_masks) return fail(IRIS_ERR_INVALID, "row range beyond loaded masks");
+    DeviceGuard g(db->device);
+    int rc = ensure_stage(db);
+    if (rc) return rc;
+    const uint64_t step = kStageRows * 16;
+    for (uint64_t off = 0; off < n; off += step) {
+        const uint64_t m = std::min(step, n - off);
+        CK(launch_untile_masks(db->d_masks, row_begin + off, m, static_cast<uint8_t*>(db->d_stage), db->stream));
+        CK(cudaMemcpyAsync(out + off * IRIS_LIMBS, db->d_stage, m * IRIS_MASK_BYTES, cudaMemcpyDeviceToHost, db->stream));
+        CK(cudaStreamSynchronize(db->stream));
+    }
+    return IRIS_OK;
+}
+
+// ------------------------------------------------------------------------------------ scan core
+static int ensure_result_buffers(iris_db* db, uint64_t rows) {
+    if (db->res_rows >= rows) return IRIS_OK;
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(db->d_res[b][k]);
+            db->d_res[b][k] = nullptr;
+        }
+    db->res_rows = 0;
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 2; ++k) CK(cudaMalloc(&db->d_res[b][k], rows * kOutRowBytes + 64));
+    db->res_rows = rows;
+    return IRIS_OK;
+}
+
+// qd / qm: prepared operand images (nullptr = that half is not computed).
+static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t row_begin, uint64_t row_end,
+                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    if (!qd && !qm) return fail(IRIS_ERR_INVALID, "no engine given");
+    if (row_begin > row_end) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    if (qd) {
+        if (!db->d_shares) return fail(IRIS_ERR_STATE, "shard holds no shares");
+        if (row_end > db->n_shares) return fail(IRIS_ERR_INVALID, "row_end %llu beyond %llu loaded shares", (unsigned long long)row_end, (unsigned long long)db->n_shares);
+        if (!dist_out && row_end > row_begin) return fail(IRIS_ERR_INVALID, "distances output is NULL");
+    }
+    if (qm) {
+        if (!db->d_masks) return fail(IRIS_ERR_STATE, "shard holds no masks");
+        if (row_end > db->n_masks) return fail(IRIS_ERR_INVALID, "row_end %llu beyond %llu loaded masks", (unsigned long long)row_end, (unsigned long long)db->n_masks);
+        if (!den_out && row_end > row_begin) return fail(IRIS_ERR_INVALID, "denominators output is NULL");
+    }
+    if (row_begin == row_end) return IRIS_OK;
+    DeviceGuard g(db->device);
+
+    ScanParams p{};
+    p.shares = qd ? db->d_shares : nullptr;
+    p.masks = qm ? db->d_masks : nullptr;
+    p.qd = qd;
+    p.qm = qm;
+    p.raw_out = raw_dev;
+    p.error = db->d_error;
+
+    const bool dist_dev = !qd || is_device_pointer(dist_out);
+    const bool den_dev = !qm || is_device_pointer(den_out);
+    if (dist_dev && den_dev) {
+        // results stay in HBM: one persistent launch, asynchronous on the shard's stream
+        p.dist_out = dist_out;
+        p.den_out = den_out;
+        p.row_begin = row_begin;
+        p.row_end = row_end;
+        p.tile_begin = (uint32_t)(row_begin / kTileRows);
+        p.tile_end = (uint32_t)((row_end + kTileRows - 1) / kTileRows);
+        CK(launch_scan(p, db->num_sms, db->stream));
+        return IRIS_OK;
+    }
+    if (raw_dev) return fail(IRIS_ERR_INVALID, "raw dump needs device outputs");
+
+    // host outputs: chunked scan on `stream`, D2H on `copy_stream`, double-buffered
+    const uint64_t chunk_rows = (uint64_t)db->num_sms * kResultChunkTilesPerSm * kTileRows;
+    int rc = ensure_result_buffers(db, chunk_rows + kTileRows);
+    if (rc) return rc;
+    const uint64_t aligned0 = row_begin / kTileRows * kTileRows;
+    uint64_t cb = row_begin;
+    for (uint64_t i = 0; cb < row_end; ++i) {
+        const uint64_t ce = std::min(row_end, aligned0 + (i + 1) * chunk_rows);
+        const int b = (int)(i & 1);
+        if (i >= 2) CK(cudaStreamWaitEvent(db->stream, db->ev_copy[b], 0));
+        p.dist_out = qd ? (dist_dev ? dist_out + (cb - row_begin) * IRIS_ROTATIONS : db->d_res[b][0]) : nullptr;
+        p.den_out = qm ? (den_dev ? den_out + (cb - row_begin) * IRIS_ROTATIONS : db->d_res[b][1]) : nullptr;
+        p.row_begin = cb;
+        p.row_end = ce;
+        p.tile_begin = (uint32_t)(cb / kTileRows);
+        p.tile_end = (uint32_t)((ce + kTileRows - 1) / kTileRows);
+        CK(launch_scan(p, db->num_sms, db->stream));
+        CK(cudaEventRecord(db->ev_scan[b], db->stream));
+        CK(cudaStreamWaitEvent(db->copy_stream, db->ev_scan[b], 0));
+        const size_t bytes = (ce - cb) * kOutRowBytes;
+        if (qd && !dist_dev)
+            CK(cudaMemcpyAsync(dist_out + (cb - row_begin) * IRIS_ROTATIONS, db->d_res[b][0], bytes, cudaMemcpyDeviceToHost, db->copy_stream));
+        if (qm && !den_dev)
+            CK(cudaMemcpyAsync(den_out + (cb - row_begin) * IRIS_ROTATIONS, db->d_res[b][1], bytes, cudaMemcpyDeviceToHost, db->copy_stream));
+        CK(cudaEventRecord(db->ev_copy[b], db->copy_stream));
+        cb = ce;
+    }
+    CK(cudaStreamSynchronize(db->copy_stream));
+    CK(cudaStreamSynchronize(db->stream));
+    return check_error_flag(db);
+}
+
+// ------------------------------------------------------------------------------------ engines
+static int require_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(IRIS_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(IRIS_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    return IRIS_OK;
+}
+
+extern "C" int iris_distance_engine_new(int device, const uint16_t* query, iris_distance_engine** out) {
+    if (!query || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
+    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    auto body = [&]() -> int {
+        int r = pooled_alloc(g_pool.q16, device, IRIS_BITS * sizeof(uint16_t), reinterpret_cast<void**>(&e->d_query));
+        if (r) return r;
+        r = pooled_alloc(g_pool.qd, device, kQdBytes, reinterpret_cast<void**>(&e->d_qd));
+        if (r) return r;
+        CK(cudaMemcpyAsync(e->d_query, query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDefault, cudaStreamPerThread));
+        CK(launch_prep_distance_query(e->d_query, e->d_qd, cudaStreamPerThread));
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        return IRIS_OK;
+    };
+    rc = body();
+    if (rc) {
+        std::string keep = g_last_error;
+        iris_distance_engine_free(e);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = e;
+    return IRIS_OK;
+}
+
+extern "C" int iris_distance_engine_free(iris_distance_engine* e) {
+    if (!e) return IRIS_OK;
+    DeviceGuard g(e->device);
+    if (e->scratch) iris_db_destroy(e->scratch);
+    g_pool.give(g_pool.q16, e->device, e->d_query);
+    g_pool.give(g_pool.qd, e->device, e->d_qd);
+    delete e;
+    return IRIS_OK;
+}
+
+extern "C" int iris_masks_engine_new(int device, const uint64_t* query_mask, iris_masks_engine** out) {
+    if (!query_mask || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    iris_masks_engine* e = new (std::nothrow) iris_masks_engine();
+    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    auto body = [&]() -> int {
+        int r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&e->d_qmask));
+        if (r) return r;
+        r = pooled_alloc(g_pool.qm, device, kQmBytes, reinterpret_cast<void**>(&e->d_qm));
+        if (r) return r;
+        CK(cudaMemcpyAsync(e->d_qmask, query_mask, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+        CK(launch_prep_mask_query(e->d_qmask, e->d_qm, cudaStreamPerThread));
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        return IRIS_OK;
+    };
+    rc = body();
+    if (rc) {
+        std::string keep = g_last_error;
+        iris_masks_engine_free(e);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = e;
+    return IRIS_OK;
+}
+
+extern "C" int iris_masks_engine_free(iris_masks_engine* e) {
+    if (!e) return IRIS_OK;
+    DeviceGuard g(e->device);
+    if (e->scratch) iris_db_destroy(e->scratch);
+    g_pool.give(g_pool.q8, e->device, e->d_qmask);
+    g_pool.give(g_pool.qm, e->device, e->d_qm);
+    delete e;
+    return IRIS_OK;
+}
+
+static constexpr uint64_t kScratchRows = 4096;
+
+extern "C" int iris_distance_engine_batch_process(iris_distance_engine* e, uint16_t* out, uint64_t out_len,
+                                                  const uint16_t* db, uint64_t db_len) {
+    if (!e) return fail(IRIS_ERR_INVALID, "engine is NULL");
+    // reference: assert_eq!(out.len(), db.len())  (src/lib.rs:43)
+    if (out_len != db_len) return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)db_len);
+    if (db_len == 0) return IRIS_OK;
+    if (!out || !db) return fail(IRIS_ERR_INVALID, "NULL slice");
+    if (!e->scratch) {
+        int rc = iris_db_create(e->device, kScratchRows, IRIS_DB_SHARES, &e->scratch);
+        if (rc) return rc;
+    }
+    for (uint64_t off = 0; off < db_len; off += kScratchRows) {
+        const uint64_t m = std::min(kScratchRows, db_len - off);
+        iris_db_clear(e->scratch);
+        int rc = iris_db_append_shares(e->scratch, db + off * IRIS_BITS, m);
+        if (rc) return rc;
+        rc = scan_core(e->scratch, e->d_qd, nullptr, 0, m, out + off * IRIS_ROTATIONS, nullptr, nullptr);
+        if (rc) return rc;
+        rc = iris_db_synchronize(e->scratch);
+        if (rc) return rc;
+    }
+    return IRIS_OK;
+}
+
+extern "C" int iris_masks_engine_batch_process(iris_masks_engine* e, uint16_t* out, uint64_t out_len,
+                                               const uint64_t* db, uint64_t db_len) {
+    if (!e) return fail(IRIS_ERR_INVALID, "engine is NULL");
+    // reference: assert_eq!(out.len(), db.len())  (src/lib.rs:70)
+    if (out_len != db_len) return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)db_len);
+    if (db_len == 0) return IRIS_OK;
+    if (!out || !db) return fail(IRIS_ERR_INVALID, "NULL slice");
+    const uint64_t rows = kScratchRows * 16;
+    if (!e->scratch) {
+        int rc = iris_db_create(e->device, rows, IRIS_DB_MASKS, &e->scratch);
+        if (rc) return rc;
+    }
+    for (uint64_t off = 0; off < db_len; off += rows) {
+        const uint64_t m = std::min(rows, db_len - off);
+        iris_db_clear(e->scratch);
+        int rc = iris_db_append_masks(e->scratch, db + off * IRIS_LIMBS, m);
+        if (rc) return rc;
+        rc = scan_core(e->scratch, nullptr, e->d_qm, 0, m, nullptr, out + off * IRIS_ROTATIONS, nullptr);
+        if (rc) return rc;
+        rc = iris_db_synchronize(e->scratch);
+        if (rc) return rc;
+    }
+    return IRIS_OK;
+}
+
+extern "C" int iris_distance_engine_batch_process_resident(iris_distance_engine* e, uint16_t* out, uint64_t out_len,
+                                                           iris_db* db, uint64_t row_begin, uint64_t row_end) {
+    if (!e || !db) return fail(IRIS_ERR_INVALID, "NULL handle");
+    if (e->device != db->device) return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
+    if (row_end < row_begin || out_len != row_end - row_begin)
+        return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)(row_end - row_begin));
+    return scan_core(db, e->d_qd, nullptr, row_begin, row_end, out, nullptr, nullptr);
+}
+
+extern "C" int iris_masks_engine_batch_process_resident(iris_masks_engine* e, uint16_t* out, uint64_t out_len,
+                                                        iris_db* db, uint64_t row_begin, uint64_t row_end) {
+    if (!e || !db) return fail(IRIS_ERR_INVALID, "NULL handle");
+    if (e->device != db->device) return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
+    if (row_end < row_begin || out_len != row_end - row_begin)
+        return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)(row_end - row_begin));
+    return scan_core(db, nullptr, e->d_qm, row_begin, row_end, nullptr, out, nullptr);
+}
+
+extern "C" int iris_match_resident(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
+                                   uint64_t row_end, uint16_t* distances_out, uint16_t* denominators_out) {
+    if (!db || (!de && !me)) return fail(IRIS_ERR_INVALID, "NULL handle");
+    if ((de && de->device != db->device) || (me && me->device != db->device))
+        return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
+    return scan_core(db, de ? de->d_qd : nullptr, me ? me->d_qm : nullptr, row_begin, row_end, distances_out,
+                     denominators_out, nullptr);
+}
+
+extern "C" int iris_distances(int device, const uint16_t* query, const uint16_t* entry, uint16_t* out) {
+    if (!query || !entry || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    iris_distance_engine* e = nullptr;
+    int rc = iris_distance_engine_new(device, query, &e);
+    if (rc) return rc;
+    rc = iris_distance_engine_batch_process(e, out, 1, entry, 1);
+    std::string keep = g_last_error;
+    iris_distance_engine_free(e);
+    g_last_error = keep;
+    return rc;
+}
+
+extern "C" int iris_denominators(int device, const uint64_t* query, const uint64_t* entry, uint16_t* out) {
+    if (!query || !entry || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    iris_masks_engine* e = nullptr;
+    int rc = iris_masks_engine_new(device, query, &e);
+    if (rc) return rc;
+    rc = iris_masks_engine_batch_process(e, out, 1, entry, 1);
+    std::string keep = g_last_error;
+    iris_masks_engine_free(e);
+    g_last_error = keep;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------ per-pair arch entry points
+template <typename T, typename F>
+static int dot_pair(int device, const T* a, const T* b, size_t bytes, uint16_t* out, F launch) {
+    if (!a || !b || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(&d, 2 * bytes + 16));
+    int result = IRIS_OK;
+    auto body = [&]() -> int {
+        CK(cudaMemcpyAsync(d, a, bytes, cudaMemcpyDefault, cudaStreamPerThread));
+        CK(cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyDefault, cudaStreamPerThread));
+        CK(launch(reinterpret_cast<const T*>(d), reinterpret_cast<const T*>(d + bytes), reinterpret_cast<uint16_t*>(d + 2 * bytes), cudaStreamPerThread));
+        CK(cudaMemcpyAsync(out, d + 2 * bytes, sizeof(uint16_t), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        return IRIS_OK;
+    };
+    result = body();
+    cudaFree(d);
+    return result;
+}
+
+extern "C" int iris_dot_u16(int device, const uint16_t* a, const uint16_t* b, uint16_t* out) {
+    return dot_pair<uint16_t>(device, a, b, IRIS_BITS * sizeof(uint16_t), out, launch_dot_u16);
+}
+extern "C" int iris_dot_bool(int device, const uint64_t* a, const uint64_t* b, uint16_t* out) {
+    return dot_pair<uint64_t>(device, a, b, IRIS_LIMBS * sizeof(uint64_t), out, launch_dot_bool);
+}
+
+// ------------------------------------------------------------------------------------ verification helpers
+extern "C" int iris_check_distances_simt(iris_db* db, const uint16_t* query, uint64_t row_begin, uint64_t row_end,
+                                         uint16_t* out) {
+    if (!db || !query || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!db->d_shares || row_end > db->n_shares || row_begin > row_end) return fail(IRIS_ERR_INVALID, "bad row range");
+    DeviceGuard g(db->device);
+    uint16_t* d_q = nullptr;
+    uint16_t* d_o = nullptr;
+    const uint64_t n = row_end - row_begin;
+    const bool out_dev = is_device_pointer(out);
+    CK(cudaMalloc(&d_q, IRIS_BITS * sizeof(uint16_t)));
+    if (!out_dev) CK(cudaMalloc(&d_o, n * kOutRowBytes + 16));
+    auto body = [&]() -> int {
+        CK(cudaMemcpyAsync(d_q, query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDefault, db->stream));
+        CK(launch_simt_distances(db->d_shares, d_q, row_begin, row_end, out_dev ? out : d_o, db->stream));
+        if (!out_dev) CK(cudaMemcpyAsync(out, d_o, n * kOutRowBytes, cudaMemcpyDeviceToHost, db->stream));
+        CK(cudaStreamSynchronize(db->stream));
+        return IRIS_OK;
+    };
+    int rc = body();
+    cudaFree(d_q);
+    cudaFree(d_o);
+    return rc;
+}
+
+extern "C" int iris_check_denominators_simt(iris_db* db, const uint64_t* query_mask, uint64_t row_begin,
+                                            uint64_t row_end, uint16_t* out) {
+    if (!db || !query_mask || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!db->d_masks || row_end > db->n_masks || row_begin > row_end) return fail(IRIS_ERR_INVALID, "bad row range");
+    DeviceGuard g(db->device);
+    uint8_t* d_q = nullptr;
+    uint16_t* d_o = nullptr;
+    const uint64_t n = row_end - row_begin;
+    const bool out_dev = is_device_pointer(out);
+    CK(cudaMalloc(&d_q, IRIS_MASK_BYTES));
+    if (!out_dev) CK(cudaMalloc(&d_o, n * kOutRowBytes + 16));
+    auto body = [&]() -> int {
+        CK(cudaMemcpyAsync(d_q, query_mask, IRIS_MASK_BYTES, cudaMemcpyDefault, db->stream));
+        CK(launch_simt_denominators(db->d_masks, d_q, row_begin, row_end, out_dev ? out : d_o, db->stream));
+        if (!out_dev) CK(cudaMemcpyAsync(out, d_o, n * kOutRowBytes, cudaMemcpyDeviceToHost, db->stream));
+        CK(cudaStreamSynchronize(db->stream));
+        return IRIS_OK;
+    };
+    int rc = body();
+    cudaFree(d_q);
+    cudaFree(d_o);
+    return rc;
+}
+
+extern "C" int iris_debug_raw_accumulators(iris_distance_engine* de, iris_masks_engine* me, iris_db* db,
+                                           uint64_t row_begin, uint64_t row_end, int32_t* raw_out) {
+    if (!db || !raw_out || (!de && !me)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (row_begin % kTileRows) return fail(IRIS_ERR_INVALID, "row_begin must be a multiple of 128");
+    if (row_end <= row_begin) return fail(IRIS_ERR_INVALID, "empty range");
+    DeviceGuard g(db->device);
+    const uint64_t tiles = (row_end - row_begin + kTileRows - 1) / kTileRows;
+    const uint64_t n = row_end - row_begin;
+    int32_t* d_raw = nullptr;
+    uint16_t* d_o = nullptr;
+    CK(cudaMalloc(&d_raw, tiles * kTileRows * 128 * sizeof(int32_t)));
+    CK(cudaMalloc(&d_o, 2 * (n * kOutRowBytes + 64)));
+    auto body = [&]() -> int {
+        CK(cudaMemsetAsync(d_raw, 0xEE, tiles * kTileRows * 128 * sizeof(int32_t), db->stream));
+        uint16_t* d_den = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(d_o) + (n * kOutRowBytes + 63) / 64 * 64);
+        int rc = scan_core(db, de ? de->d_qd : nullptr, me ? me->d_qm : nullptr, row_begin, row_end, d_o, d_den, d_raw);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(raw_out, d_raw, tiles * kTileRows * 128 * sizeof(int32_t), cudaMemcpyDeviceToHost, db->stream));
+        CK(cudaStreamSynchronize(db->stream));
+        return check_error_flag(db);
+    };
+    int rc = body();
+    cudaFree(d_raw);
+    cudaFree(d_o);
+    return rc;
+}

@@ -1,0 +1,58 @@
+// Internal launch API between the C-ABI host runtime (iris_abi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "iris_layout.h"
+
+namespace iris {
+
+struct ScanParams {
+    const uint8_t* shares;   // tiled share planes (nullptr when not scanning distances)
+    const uint8_t* masks;    // tiled packed masks (nullptr when not scanning denominators)
+    const uint8_t* qd;       // prepared distance operand image (kQdBytes)
+    const uint8_t* qm;       // prepared mask operand image (kQmBytes)
+    uint16_t* dist_out;      // [row_end-row_begin][31] u16, row-major packed (62 B rows)
+    uint16_t* den_out;       // same
+    int32_t* raw_out;        // optional debug dump: [tiles*128][128] raw s32 accumulators
+    uint64_t row_begin;      // rows outside [row_begin,row_end) are computed but not stored
+    uint64_t row_end;
+    uint32_t tile_begin;     // = row_begin / 128
+    uint32_t tile_end;       // = ceil(row_end / 128)
+    int* error;              // device int, set by the watchdog
+};
+
+// Launches the persistent tcgen05 scan.  Mode is derived from which of shares/masks is non-null.
+cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
+
+// Query preparation (K3): reference DistanceEngine::new / MasksEngine::new (src/lib.rs:33-40, 60-67).
+cudaError_t launch_prep_distance_query(const uint16_t* d_query, uint8_t* d_qd, cudaStream_t stream);
+cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, cudaStream_t stream);
+
+// Loader: reference-layout rows (device staging) -> tiled HBM image, starting at global row row0.
+cudaError_t launch_retile_shares(const uint16_t* d_rows, uint64_t n, uint8_t* d_shares, uint64_t row0,
+                                 cudaStream_t stream);
+cudaError_t launch_retile_masks(const uint8_t* d_rows, uint64_t n, uint8_t* d_masks, uint64_t row0,
+                                cudaStream_t stream);
+// Inverse of the loader (tests, debugging): tiled image -> reference-layout rows.
+cudaError_t launch_untile_shares(const uint8_t* d_shares, uint64_t row0, uint64_t n, uint16_t* d_rows,
+                                 cudaStream_t stream);
+cudaError_t launch_untile_masks(const uint8_t* d_masks, uint64_t row0, uint64_t n, uint8_t* d_rows,
+                                cudaStream_t stream);
+// Synthetic database fill directly in the tiled layout; row ids row_id0.. stored at rows row0..
+cudaError_t launch_generate(uint8_t* d_shares, uint8_t* d_masks, uint64_t seed, uint64_t row_id0, uint64_t row0,
+                            uint64_t n, cudaStream_t stream);
+
+// CUDA-core cross-check kernels over the same tiled image (not the product path; used to verify
+// the tensor path at full size on the GPU and to serve the per-pair arch entry points).
+cudaError_t launch_simt_distances(const uint8_t* d_shares, const uint16_t* d_query, uint64_t row_begin,
+                                  uint64_t row_end, uint16_t* d_out, cudaStream_t stream);
+cudaError_t launch_simt_denominators(const uint8_t* d_masks, const uint8_t* d_qmask, uint64_t row_begin,
+                                     uint64_t row_end, uint16_t* d_out, cudaStream_t stream);
+cudaError_t launch_dot_u16(const uint16_t* d_a, const uint16_t* d_b, uint16_t* d_out, cudaStream_t stream);
+cudaError_t launch_dot_bool(const uint64_t* d_a, const uint64_t* d_b, uint16_t* d_out, cudaStream_t stream);
+
+// Number of kernels launched by this library since load (bench.py's gpu_launches).
+uint64_t launch_count();
+
+}  // namespace iris
