@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/iris_b200.h declares, and fails LOUDLY (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "iris_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(iris_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_entry_points():
+    names = declared_functions()
+    for required in ("iris_dot_u16", "iris_dot_bool", "iris_distance_engine_new", "iris_distance_engine_batch_process",
+                     "iris_masks_engine_new", "iris_masks_engine_batch_process", "iris_distances", "iris_denominators"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    import mpc_iris_code_b200 as iris
+    from mpc_iris_code_b200 import build
+
+    build.build()
+    L = ctypes.CDLL(iris.library_path())
+    missing = [n for n in declared_functions() if not hasattr(L, n)]
+    assert not missing, missing
+    iris.lib()  # binds argtypes for every function the wrapper uses
+
+
+def test_sass_contains_tcgen05_and_bulk_copy():
+    """The product kernel must be the tensor-core one: UTCIMMA (tcgen05.mma kind::i8), LDTM (tcgen05.ld),
+    UBLKCP (cp.async.bulk) in the SASS of the shipped library."""
+    import shutil
+    import subprocess
+
+    import mpc_iris_code_b200 as iris
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", iris.library_path()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCIMMA", "LDTM", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import mpc_iris_code_b200 as iris
+
+    q = np.zeros(iris.BITS, np.uint16)
+    m = np.zeros(iris.LIMBS, np.uint64)
+    for call in (lambda: iris.Database(128), lambda: iris.DistanceEngine(q), lambda: iris.MasksEngine(m),
+                 lambda: iris.dot_u16(q, q), lambda: iris.dot_bool(m, m), lambda: iris.distances(q, q),
+                 lambda: iris.denominators(m, m)):
+        with pytest.raises(iris.IrisError) as ei:
+            call()
+        assert ei.value.code == -2
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mpc-iris-code_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "iris_oracle" not in text, f
+    for f in ("include/iris_b200.h",):
+        assert "oracle/" not in open(os.path.join(ROOT, f)).read().replace("oracle/iris_oracle.c restates the generator", "")
+
+
+def test_wrapper_validates_buffers():
+    import mpc_iris_code_b200 as iris
+    from mpc_iris_code_b200 import api
+
+    with pytest.raises(TypeError):
+        api._ptr(np.zeros(iris.BITS, np.int32), np.uint16, iris.BITS, "q")
+    with pytest.raises(ValueError):
+        api._ptr(np.zeros(10, np.uint16), np.uint16, iris.BITS, "q")
+    with pytest.raises(ValueError):
+        api._ptr(np.zeros((4, iris.BITS), np.uint16)[:, ::2], np.uint16, 1, "q")

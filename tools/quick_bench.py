@@ -25,8 +25,8 @@ def main():
     q = O.encode(O.gen_mask_rows(5, 0, 1)[0], O.gen_mask_rows(5, 1, 1)[0])
     qm = O.gen_mask_rows(5, 1, 1)[0]
     de, me = iris.DistanceEngine(q), iris.MasksEngine(qm)
-    dist = torch.empty((n, 31), dtype=torch.uint16, device="cuda")
-    den = torch.empty((n, 31), dtype=torch.uint16, device="cuda")
+    dist = torch.empty((n, 31), dtype=torch.int16, device="cuda")
+    den = torch.empty((n, 31), dtype=torch.int16, device="cuda")
     for name, a, b, bytes_per_row in (("fused", de, me, 27200 + 124), ("distances", de, None, 25600 + 62), ("denominators", None, me, 1600 + 62)):
         for _ in range(3):
             iris.match(a, b, db, 0, n, dist, den)
