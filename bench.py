@@ -57,8 +57,9 @@ def make_query():
 
 
 # ----------------------------------------------------------------------------------- CPU arm
-def time_oracle(rows: int, threads: int, q, qm, repeat: int = 1):
-    """Seconds for one fused pass (distances + denominators) of the CPU oracle over `rows` rows."""
+def time_oracle(rows: int, threads: int, q, qm, seconds: float = 0.0):
+    """Runs fused passes (distances + denominators) of the CPU oracle over a `rows`-row sample until `seconds`
+    of wall time have accumulated (at least one pass); returns (passes, total seconds)."""
     import oracle as O
 
     shares = O.gen_share_rows(SEED, 0, rows, threads=threads)
@@ -67,32 +68,32 @@ def time_oracle(rows: int, threads: int, q, qm, repeat: int = 1):
     mrot = O.mask_rotations(qm)
     out_d = np.empty((rows, 31), np.uint16)
     out_n = np.empty((rows, 31), np.uint16)
-    best = float("inf")
-    for _ in range(repeat):
+    passes, total = 0, 0.0
+    while passes == 0 or total < seconds:
         t0 = time.perf_counter()
         O.distance_batch_prepared(rot, shares, out_d, threads)
         O.masks_batch_prepared(mrot, masks, out_n, threads)
-        best = min(best, time.perf_counter() - t0)
-    return best
+        total += time.perf_counter() - t0
+        passes += 1
+    return passes, total
 
 
 def cpu_baseline(target_seconds: float, q, qm):
     cores = os.cpu_count() or 1
-    probe_rows = 64 * cores
-    time_oracle(probe_rows, cores, q, qm)  # warm-up (page faults, OpenMP pool)
-    t = time_oracle(probe_rows, cores, q, qm)
-    rows = int(max(probe_rows, min(400_000, probe_rows * target_seconds / max(t, 1e-6))))
-    t_all = time_oracle(rows, cores, q, qm)
-    rows1 = max(64, rows // (cores * 8))
-    t_one = time_oracle(rows1, 1, q, qm)
+    rows = 4096 * cores                            # bounded sample: 1.8 GB at 16 cores, far beyond the CPU caches
+    time_oracle(256 * cores, cores, q, qm)         # warm-up (page faults, OpenMP pool)
+    passes, t_all = time_oracle(rows, cores, q, qm, target_seconds)
+    rows1 = 2048
+    p1, t_one = time_oracle(rows1, 1, q, qm, min(3.0, target_seconds / 3))
     return {
-        "value": rows / t_all,
+        "value": rows * passes / t_all,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
-        "sample": f"{rows} of the workload's rows x 31 rotations, distances+denominators, C port of src/arch/generic.rs "
-                  f"(gcc -O3 -march=native, OpenMP static over rows = rayon par_iter), {t_all:.2f} s",
-        "single_thread_value": rows1 / t_one,
+        "sample": f"{passes} passes over {rows} of the workload's rows x 31 rotations, distances+denominators, C port of "
+                  f"src/arch/generic.rs + engine loops (gcc -O3 -march=native, OpenMP static over rows = rayon par_iter), "
+                  f"{t_all:.1f} s of wall time on {cores} threads",
+        "single_thread_value": rows1 * p1 / t_one,
     }
 
 
@@ -102,9 +103,9 @@ def run_reference(args):
         return
     q, qm = make_query()
     cores = os.cpu_count() or 1
-    probe = 64 * cores
+    probe = 256 * cores
     time_oracle(probe, cores, q, qm)
-    t = time_oracle(probe, cores, q, qm)
+    t = time_oracle(probe, cores, q, qm)[1]
     total = args.steps + args.warmup
     per_step_target = min(4.0, 150.0 / max(total, 1))
     rows = int(max(probe, min(200_000, probe * per_step_target / max(t, 1e-6))))

@@ -202,7 +202,7 @@ def test_errors_mirror_reference_asserts(iris, small):
     with iris.Database(10, shares=True, masks=False) as only_shares:
         only_shares.generate(1, 0, 10)
         with pytest.raises(iris.IrisError) as ei:
-            me.batch_process(np.zeros((10, 31), np.uint16), only_shares)
+            me.batch_process(np.zeros((10, 31), np.uint16), only_shares, 0, 10)
         assert ei.value.code == -4
     # empty slices are fine (rayon over zero rows)
     de.batch_process(np.zeros((0, 31), np.uint16), np.zeros((0, O.BITS), np.uint16))
