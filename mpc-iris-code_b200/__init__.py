@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     denominators,
     device_count,
     distances,
+    distances_batch,
     dot_bool,
     dot_u16,
     launch_count,

@@ -73,6 +73,7 @@ def lib():
         "iris_masks_engine_batch_process": [vp, vp, u64, vp, u64],
         "iris_masks_engine_batch_process_resident": [vp, vp, u64, vp, u64, u64],
         "iris_match_resident": [vp, vp, vp, u64, u64, vp, vp],
+        "iris_distances_batch_resident": [vp, u32, vp, u64, u64, vp],
         "iris_distances": [i32, vp, vp, vp],
         "iris_denominators": [i32, vp, vp, vp],
         "iris_check_distances_simt": [vp, vp, u64, u64, vp],
@@ -331,6 +332,14 @@ def match(distance_engine: Optional[DistanceEngine], masks_engine: Optional[Mask
         db._h, row_begin, row_end,
         _ptr(distances_out, np.uint16, n, "distances_out") if distance_engine else None,
         _ptr(denominators_out, np.uint16, n, "denominators_out") if masks_engine else None))
+
+
+def distances_batch(engines, db: Database, row_begin: int, row_end: int, out) -> None:
+    """All `engines` (DistanceEngine list) against rows [row_begin,row_end) as one tensor-core GEMM;
+    out = [len(engines)][rows][31] u16, numpy (host) or torch CUDA tensor."""
+    n = len(engines) * (row_end - row_begin) * ROTATIONS
+    arr = (ctypes.c_void_p * len(engines))(*[e._h.value for e in engines])
+    _check(lib().iris_distances_batch_resident(arr, len(engines), db._h, row_begin, row_end, _ptr(out, np.uint16, n, "out")))
 
 
 def raw_accumulators(distance_engine, masks_engine, db: Database, row_begin: int, row_end: int) -> np.ndarray:

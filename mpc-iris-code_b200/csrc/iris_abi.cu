@@ -99,6 +99,7 @@ struct iris_distance_engine {
     int device = 0;
     uint16_t* d_query = nullptr;
     uint8_t* d_qd = nullptr;
+    bool fits_s8 = false;            // every element is a sign-extended byte (true for encode() output)
     iris_db* scratch = nullptr;      // for the host-slice batch_process
 };
 
@@ -161,7 +162,8 @@ extern "C" int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags
     if (!db) return fail(IRIS_ERR_NOMEM, "host allocation failed");
     db->device = device;
     db->flags = flags;
-    db->capacity = (capacity_rows + kTileRows - 1) / kTileRows * kTileRows;
+    // whole 256-row pair tiles (the batched kernel works on pairs of 128-row tiles), zero filled
+    db->capacity = (capacity_rows + 2 * kTileRows - 1) / (2 * kTileRows) * (2 * kTileRows);
     const uint64_t tiles = db->capacity / kTileRows;
     int rc = IRIS_OK;
     auto body = [&]() -> int {
@@ -476,6 +478,17 @@ extern "C" int iris_distance_engine_new(int device, const uint16_t* query, iris_
         if (r) return r;
         CK(cudaMemcpyAsync(e->d_query, query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDefault, cudaStreamPerThread));
         CK(launch_prep_distance_query(e->d_query, e->d_qd, cudaStreamPerThread));
+        // classify the query for the batched path: sign-extended bytes need only two limb products
+        std::vector<uint16_t> host(IRIS_BITS);
+        const uint16_t* hq = query;
+        if (is_device_pointer(query)) {
+            CK(cudaMemcpyAsync(host.data(), e->d_query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+            CK(cudaStreamSynchronize(cudaStreamPerThread));
+            hq = host.data();
+        }
+        bool s8 = true;
+        for (int k = 0; k < IRIS_BITS; ++k) s8 &= (hq[k] <= 0x7F) || (hq[k] >= 0xFF80);
+        e->fits_s8 = s8;
         CK(cudaStreamSynchronize(cudaStreamPerThread));
         return IRIS_OK;
     };
@@ -639,6 +652,60 @@ extern "C" int iris_denominators(int device, const uint64_t* query, const uint64
     std::string keep = g_last_error;
     iris_masks_engine_free(e);
     g_last_error = keep;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------ batched queries (dense GEMM)
+extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engines, uint32_t num_queries, iris_db* db,
+                                             uint64_t row_begin, uint64_t row_end, uint16_t* out) {
+    if (!engines || !db) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (num_queries == 0) return IRIS_OK;
+    if (row_begin > row_end) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    if (!db->d_shares) return fail(IRIS_ERR_STATE, "shard holds no shares");
+    if (row_end > db->n_shares) return fail(IRIS_ERR_INVALID, "row_end beyond loaded shares");
+    if (row_begin == row_end) return IRIS_OK;
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    for (uint32_t i = 0; i < num_queries; ++i) {
+        if (!engines[i]) return fail(IRIS_ERR_INVALID, "engine %u is NULL", i);
+        if (engines[i]->device != db->device) return fail(IRIS_ERR_INVALID, "engine %u lives on another device", i);
+    }
+    DeviceGuard g(db->device);
+    const uint64_t rows = row_end - row_begin;
+    const bool out_dev = is_device_pointer(out);
+    uint16_t* d_out = out;
+    const size_t out_bytes = (size_t)num_queries * rows * kOutRowBytes;
+    if (!out_dev) CK(cudaMalloc(&d_out, out_bytes + 64));
+    auto body = [&]() -> int {
+        for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxBatchQueries) {
+            const uint32_t nq = std::min<uint32_t>(kMaxBatchQueries, num_queries - q0);
+            BatchParams p{};
+            p.shares = db->d_shares;
+            bool all_s8 = true;
+            for (uint32_t i = 0; i < nq; ++i) {
+                p.qd[i] = engines[q0 + i]->d_qd;
+                all_s8 &= engines[q0 + i]->fits_s8;
+            }
+            p.out = d_out + (size_t)q0 * rows * IRIS_ROTATIONS;
+            p.row_begin = row_begin;
+            p.row_end = row_end;
+            p.pair_begin = (uint32_t)(row_begin / (2 * kTileRows));
+            p.pair_end = (uint32_t)((row_end + 2 * kTileRows - 1) / (2 * kTileRows));
+            p.num_queries = nq;
+            p.error = db->d_error;
+            CK(launch_batch_distances(p, all_s8, db->num_sms, db->stream));
+        }
+        if (!out_dev) {
+            CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, db->stream));
+            CK(cudaStreamSynchronize(db->stream));
+            return check_error_flag(db);
+        }
+        return IRIS_OK;
+    };
+    int rc = body();
+    if (!out_dev) {
+        cudaStreamSynchronize(db->stream);
+        cudaFree(d_out);
+    }
     return rc;
 }
 

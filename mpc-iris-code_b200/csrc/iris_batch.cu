@@ -1,0 +1,257 @@
+// Batched queries x rotations vs the resident database as a dense int8 GEMM (BASELINE config 4).
+//
+//   D[rows x (8 queries x 32 rotations)] = DB[rows x 12800] . Q[(8 x 32) x 12800]^T   per limb product
+//
+// Same arithmetic as the scan (iris_kernels.cu): S00 = d_lo.q_lo, S1 = d_lo.q_hi + d_hi.q_lo (two UMMAs
+// accumulating into the same TMEM columns), dist = (S00 + (S1 << 8)) & 0xFFFF.  When every query of a
+// group is representable as a signed byte (always true for encode() output {0,1,0xFFFF}, src/lib.rs:16-26)
+// the q_lo plane IS the s8 value and only two products are needed: S0 = d_lo.q_s, S1 = d_hi.q_s.
+//
+// One CTA PAIR (tcgen05 cta_group::2, UMMA M = 256, N = 256) works on 256 database rows x 8 queries:
+// each CTA streams its own 128-row share tile (32 KiB per K-chunk) and HALF of the query operand
+// (4 queries: 16 KiB q_lo + 16 KiB q_hi), so a K-chunk of 128 costs 64 KiB of L2->SM traffic per CTA for
+// 2 x 256 x 256 x 128 x 3/2 MACs.  The 2 x 256 s32 accumulator columns fill TMEM (512 columns) exactly.
+// Query groups are the fastest-varying tile index so the clusters working on one row tile hit it in L2
+// and HBM is read once per batch.
+#include <cuda_runtime.h>
+
+#include "iris_kernels.cuh"
+#include "iris_ptx.cuh"
+
+namespace iris {
+
+void count_launch_external();
+
+constexpr int kBatchStages = 3;
+constexpr int kBatchQTile = 8;                         // queries per cluster tile
+constexpr int kBatchBBytes = 4 * kQTileBytes;          // 4 queries x 4 KiB per plane per CTA
+constexpr int kBatchStageBytes = kShareChunkBytes + 2 * kBatchBBytes;   // 64 KiB
+constexpr int kBatchOffAlo = 0;
+constexpr int kBatchOffAhi = kPlaneTileBytes;
+constexpr int kBatchOffBlo = kShareChunkBytes;
+constexpr int kBatchOffBhi = kShareChunkBytes + kBatchBBytes;
+constexpr int kBatchOutStageBytes = 8192;
+constexpr int kBatchSmemBytes = 1024 + kBatchStages * kBatchStageBytes + 2 * kBatchOutStageBytes + 512;
+constexpr int kBatchThreads = 192;                     // warps 0-3 epilogue, 4 producer, 5 UMMA issuer
+static_assert(kBatchSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
+
+enum BatchWatchdog { kWbProducer = 201, kWbFull = 202, kWbReady = 203, kWbTmemEmpty = 204, kWbEpilogue = 205 };
+
+__device__ __forceinline__ void copy_out_rows(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
+    if (b1 <= b0) return;
+    int body0 = (b0 + 15) & ~15, body1 = b1 & ~15;
+    if (body0 > body1) {
+        for (int b = b0 + 2 * tid; b < b1; b += 2 * 128)
+            *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
+        return;
+    }
+    for (int b = b0 + 2 * tid; b < body0; b += 2 * 128)
+        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
+    for (int b = body0 + 16 * tid; b < body1; b += 16 * 128)
+        *reinterpret_cast<uint4*>(gbase + b) = *reinterpret_cast<const uint4*>(stage + b);
+    for (int b = body1 + 2 * tid; b < b1; b += 2 * 128)
+        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
+}
+
+template <bool SIGNED_Q>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
+    batch_distances_kernel(const BatchParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* const base_ptr = smem_raw + (base - raw_addr);
+    uint8_t* const out_stage_ptr = base_ptr + kBatchStages * kBatchStageBytes;
+    const uint32_t bars = base + kBatchStages * kBatchStageBytes + 2 * kBatchOutStageBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };                         // local loads landed
+    auto empty_bar = [&](int s) { return bars + 8u * (kBatchStages + s); };       // UMMAs done with the stage (both CTAs)
+    auto ready_bar = [&](int s) { return bars + 8u * (2 * kBatchStages + s); };   // leader only: both CTAs' stage landed
+    const uint32_t tfull_bar = bars + 8u * (3 * kBatchStages);                    // accumulators complete
+    const uint32_t tempty_bar = bars + 8u * (3 * kBatchStages + 1);               // leader only: both epilogues drained
+    const uint32_t tmem_slot = bars + 8u * (3 * kBatchStages + 2);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+        out_stage_ptr + 2 * kBatchOutStageBytes + 8 * (3 * kBatchStages + 2));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();            // 0 = leader (issues the UMMAs)
+    const uint32_t cluster_id = blockIdx.x >> 1;
+    const uint32_t num_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBatchStages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+            ptx::mbar_init(ready_bar(s), 2);
+        }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::mbar_init(tempty_bar, 256);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 5) ptx::tmem_alloc_2cta(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                                     // barriers of both CTAs are initialised
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const uint32_t num_groups = (p.num_queries + kBatchQTile - 1) / kBatchQTile;
+    const uint32_t num_tiles = (p.pair_end - p.pair_begin) * num_groups;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ producer (each CTA loads its own half)
+        if (lane == 0) {
+            const uint64_t pol_keep = ptx::policy_evict_last();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+                const uint32_t pair = p.pair_begin + t / num_groups;
+                const uint32_t group = t % num_groups;
+                const uint8_t* sh = p.shares + (size_t)(2 * pair + rank) * kShareTileBytes;
+                const uint8_t* q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t qi = group * kBatchQTile + 4 * rank + i;
+                    q[i] = p.qd[qi < p.num_queries ? qi : p.num_queries - 1];
+                }
+                for (int c = 0; c < kChunks; ++c) {
+                    ptx::mbar_wait_cluster(empty_bar(stage), phase ^ 1u, p.error, kWbProducer);
+                    const uint32_t sbase = base + stage * kBatchStageBytes;
+                    const uint32_t fb = full_bar(stage);
+                    ptx::mbar_arrive_expect_tx(fb, SIGNED_Q ? kShareChunkBytes + kBatchBBytes : kBatchStageBytes);
+                    ptx::bulk_g2s(sbase + kBatchOffAlo, sh + (size_t)c * kShareChunkBytes, kShareChunkBytes, fb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ptx::bulk_g2s_hint(sbase + kBatchOffBlo + i * kQTileBytes, q[i] + (size_t)c * kQdChunkBytes,
+                                           kQTileBytes, fb, pol_keep);
+                        if (!SIGNED_Q)
+                            ptx::bulk_g2s_hint(sbase + kBatchOffBhi + i * kQTileBytes,
+                                               q[i] + (size_t)c * kQdChunkBytes + kQTileBytes, kQTileBytes, fb, pol_keep);
+                    }
+                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ stage relay (both CTAs) + UMMA issue (leader)
+        if (lane == 0) {
+            constexpr uint32_t kIdescU = ptx::umma_idesc_i8_m256(256, false, false);
+            constexpr uint32_t kIdescS = ptx::umma_idesc_i8_m256(256, false, true);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                if (rank == 0) {
+                    ptx::mbar_wait_cluster(tempty_bar, (it & 1u) ^ 1u, p.error, kWbTmemEmpty);
+                    ptx::tc_fence_after();
+                }
+                for (int c = 0; c < kChunks; ++c) {
+                    ptx::mbar_wait(full_bar(stage), phase, p.error, kWbFull);
+                    ptx::mbar_arrive_cluster(ptx::mapa(ready_bar(stage), 0));      // tell the leader this half landed
+                    if (rank == 0) {
+                        ptx::mbar_wait_cluster(ready_bar(stage), phase, p.error, kWbReady);
+                        ptx::tc_fence_after();
+                        const uint32_t sbase = base + stage * kBatchStageBytes;
+#pragma unroll
+                        for (int k = 0; k < kChunkK / 32; ++k) {
+                            const uint32_t acc = (c | k) ? 1u : 0u;
+                            const uint64_t alo = ptx::umma_desc_sw128(sbase + kBatchOffAlo + 32 * k);
+                            const uint64_t ahi = ptx::umma_desc_sw128(sbase + kBatchOffAhi + 32 * k);
+                            const uint64_t blo = ptx::umma_desc_sw128(sbase + kBatchOffBlo + 32 * k);
+                            if (SIGNED_Q) {
+                                ptx::umma_i8_2cta(tmem_base + 0, alo, blo, kIdescS, acc);
+                                ptx::umma_i8_2cta(tmem_base + 256, ahi, blo, kIdescS, acc);
+                            } else {
+                                const uint64_t bhi = ptx::umma_desc_sw128(sbase + kBatchOffBhi + 32 * k);
+                                ptx::umma_i8_2cta(tmem_base + 0, alo, blo, kIdescU, acc);
+                                ptx::umma_i8_2cta(tmem_base + 256, alo, bhi, kIdescU, acc);
+                                ptx::umma_i8_2cta(tmem_base + 256, ahi, blo, kIdescU, 1u);
+                            }
+                        }
+                        ptx::umma_commit_2cta(empty_bar(stage), 3);
+                        if (c == kChunks - 1) ptx::umma_commit_2cta(tfull_bar, 3);
+                    }
+                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 0..3 of each CTA)
+        const int row = threadIdx.x;
+        const uint32_t tempty_leader = ptx::mapa(tempty_bar, 0);
+        const uint64_t rows_out = p.row_end - p.row_begin;
+        uint32_t it = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            const uint32_t pair = p.pair_begin + t / num_groups;
+            const uint32_t group = t % num_groups;
+            ptx::mbar_wait_cluster(tfull_bar, it & 1u, p.error, kWbEpilogue);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const int64_t trow0 = ((int64_t)2 * pair + rank) * kTileRows;
+            int64_t lo = (int64_t)p.row_begin - trow0, hi = (int64_t)p.row_end - trow0;
+            const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
+            const int r1 = (int)(hi < 0 ? 0 : (hi > kTileRows ? kTileRows : hi));
+            const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
+#pragma unroll 1
+            for (int g = 0; g < kBatchQTile; ++g) {
+                const uint32_t qi = group * kBatchQTile + g;
+                uint32_t a[32], b[32];
+                ptx::tmem_ld32(taddr + 32 * g, a);
+                ptx::tmem_ld32(taddr + 256 + 32 * g, b);
+                ptx::tmem_wait_ld();
+                if (g == kBatchQTile - 1) {
+                    // all accumulator columns of this CTA have been read: let the leader start the next tile
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive_cluster(tempty_leader);
+                }
+                if (qi < p.num_queries) {             // uniform over the CTA
+                    uint8_t* outq = reinterpret_cast<uint8_t*>(p.out + (size_t)qi * rows_out * IRIS_ROTATIONS);
+                    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(outq) + tile_off) & 15);
+                    uint8_t* stage_buf = out_stage_ptr + (g & 1) * kBatchOutStageBytes;
+                    uint8_t* st = stage_buf + shift + row * kOutRowBytes;
+#pragma unroll
+                    for (int j = 0; j < IRIS_ROTATIONS; ++j)
+                        *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)(a[j] + (b[j] << 8));
+                    ptx::named_bar_sync(1, 128);
+                    copy_out_rows(stage_buf, outq + tile_off - shift, (int)shift + r0 * kOutRowBytes,
+                                  (int)shift + r1 * kOutRowBytes, row);
+                    // staging buffers alternate per query: a thread can only write buffer (g&1) again after
+                    // passing the barrier of query g+1, which every thread reaches after its copy of query g.
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                                     // nobody may leave while the peer can still signal / read it
+    if (warp == 5) ptx::tmem_dealloc_2cta(tmem_base, 512);
+}
+
+template <bool SIGNED_Q>
+static cudaError_t launch_batch_t(const BatchParams& p, int num_sms, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && !configured[dev]) {
+        e = cudaFuncSetAttribute(batch_distances_kernel<SIGNED_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kBatchSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const uint32_t num_groups = (p.num_queries + kBatchQTile - 1) / kBatchQTile;
+    const uint32_t tiles = (p.pair_end - p.pair_begin) * num_groups;
+    if (tiles == 0) return cudaSuccess;
+    uint32_t clusters = (uint32_t)num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    batch_distances_kernel<SIGNED_Q><<<2 * clusters, kBatchThreads, kBatchSmemBytes, stream>>>(p);
+    count_launch_external();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_batch_distances(const BatchParams& p, bool signed_queries, int num_sms, cudaStream_t stream) {
+    if (p.num_queries == 0 || p.num_queries > kMaxBatchQueries) return cudaErrorInvalidValue;
+    return signed_queries ? launch_batch_t<true>(p, num_sms, stream) : launch_batch_t<false>(p, num_sms, stream);
+}
+
+}  // namespace iris

@@ -23,6 +23,7 @@ namespace iris {
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launch_external() { count_launch(); }
 
 // =====================================================================================
 // scan kernel

@@ -52,6 +52,20 @@ cudaError_t launch_simt_denominators(const uint8_t* d_masks, const uint8_t* d_qm
 cudaError_t launch_dot_u16(const uint16_t* d_a, const uint16_t* d_b, uint16_t* d_out, cudaStream_t stream);
 cudaError_t launch_dot_bool(const uint64_t* d_a, const uint64_t* d_b, uint16_t* d_out, cudaStream_t stream);
 
+// Batched distances (iris_batch.cu): up to kMaxBatchQueries prepared queries against rows
+// [row_begin,row_end) in one dense int8 GEMM; out = [num_queries][row_end-row_begin][31] u16 (device).
+constexpr int kMaxBatchQueries = 64;
+struct BatchParams {
+    const uint8_t* shares;
+    const uint8_t* qd[kMaxBatchQueries];   // prepared distance operand image of each query
+    uint16_t* out;
+    uint64_t row_begin, row_end;
+    uint32_t pair_begin, pair_end;         // 256-row tile range covering [row_begin,row_end)
+    uint32_t num_queries;
+    int* error;
+};
+cudaError_t launch_batch_distances(const BatchParams& p, bool signed_queries, int num_sms, cudaStream_t stream);
+
 // Number of kernels launched by this library since load (bench.py's gpu_launches).
 uint64_t launch_count();
 
