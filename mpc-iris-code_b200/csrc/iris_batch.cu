@@ -4,15 +4,21 @@
 //
 // Same arithmetic as the scan (iris_kernels.cu): S00 = d_lo.q_lo, S1 = d_lo.q_hi + d_hi.q_lo (two UMMAs
 // accumulating into the same TMEM columns), dist = (S00 + (S1 << 8)) & 0xFFFF.  When every query of a
-// group is representable as a signed byte (always true for encode() output {0,1,0xFFFF}, src/lib.rs:16-26)
+// batch is representable as a signed byte (always true for encode() output {0,1,0xFFFF}, src/lib.rs:16-26)
 // the q_lo plane IS the s8 value and only two products are needed: S0 = d_lo.q_s, S1 = d_hi.q_s.
 //
 // One CTA PAIR (tcgen05 cta_group::2, UMMA M = 256, N = 256) works on 256 database rows x 8 queries:
 // each CTA streams its own 128-row share tile (32 KiB per K-chunk) and HALF of the query operand
-// (4 queries: 16 KiB q_lo + 16 KiB q_hi), so a K-chunk of 128 costs 64 KiB of L2->SM traffic per CTA for
-// 2 x 256 x 256 x 128 x 3/2 MACs.  The 2 x 256 s32 accumulator columns fill TMEM (512 columns) exactly.
+// (4 queries: 16 KiB q_lo [+ 16 KiB q_hi]).  The 2 x 256 s32 accumulator columns fill TMEM (512 columns).
 // Query groups are the fastest-varying tile index so the clusters working on one row tile hit it in L2
 // and HBM is read once per batch.
+//
+// Cross-CTA protocol (only async-proxy data crosses CTAs, so all mbarrier traffic is cta-scope/cheap):
+//   full[s]   local   : this CTA's bulk copies of stage s landed (expect-tx)
+//   ready[s]  leader  : count 2 -- each CTA's relay thread arrives once its full[s] completed
+//   empty[s]  both    : tcgen05.commit multicast from the leader when the UMMAs reading stage s finished
+//   tfull     both    : tcgen05.commit multicast after the last K-chunk of a tile
+//   tempty    leader  : count 8 -- one arrive per epilogue warp of both CTAs once TMEM has been drained
 #include <cuda_runtime.h>
 
 #include "iris_kernels.cuh"
@@ -22,18 +28,22 @@ namespace iris {
 
 void count_launch_external();
 
-constexpr int kBatchStages = 3;
 constexpr int kBatchQTile = 8;                         // queries per cluster tile
 constexpr int kBatchBBytes = 4 * kQTileBytes;          // 4 queries x 4 KiB per plane per CTA
-constexpr int kBatchStageBytes = kShareChunkBytes + 2 * kBatchBBytes;   // 64 KiB
-constexpr int kBatchOffAlo = 0;
-constexpr int kBatchOffAhi = kPlaneTileBytes;
-constexpr int kBatchOffBlo = kShareChunkBytes;
-constexpr int kBatchOffBhi = kShareChunkBytes + kBatchBBytes;
 constexpr int kBatchOutStageBytes = 8192;
-constexpr int kBatchSmemBytes = 1024 + kBatchStages * kBatchStageBytes + 2 * kBatchOutStageBytes + 512;
-constexpr int kBatchThreads = 192;                     // warps 0-3 epilogue, 4 producer, 5 UMMA issuer
-static_assert(kBatchSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
+constexpr int kBatchThreads = 192;                     // warps 0-3 epilogue, 4 producer, 5 relay + UMMA issuer
+
+template <bool SIGNED_Q>
+struct BatchCfg {
+    static constexpr int kStageBytes = kShareChunkBytes + (SIGNED_Q ? 1 : 2) * kBatchBBytes;   // 48 / 64 KiB
+    static constexpr int kStages = SIGNED_Q ? 4 : 3;
+    static constexpr int kOffAlo = 0;
+    static constexpr int kOffAhi = kPlaneTileBytes;
+    static constexpr int kOffBlo = kShareChunkBytes;
+    static constexpr int kOffBhi = kShareChunkBytes + kBatchBBytes;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kBatchOutStageBytes + 512;
+    static_assert(kSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
+};
 
 enum BatchWatchdog { kWbProducer = 201, kWbFull = 202, kWbReady = 203, kWbTmemEmpty = 204, kWbEpilogue = 205 };
 
@@ -56,20 +66,22 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* stage, uint8_t* gba
 template <bool SIGNED_Q>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
     batch_distances_kernel(const BatchParams p) {
+    using Cfg = BatchCfg<SIGNED_Q>;
+    constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* const base_ptr = smem_raw + (base - raw_addr);
-    uint8_t* const out_stage_ptr = base_ptr + kBatchStages * kBatchStageBytes;
-    const uint32_t bars = base + kBatchStages * kBatchStageBytes + 2 * kBatchOutStageBytes;
-    auto full_bar = [&](int s) { return bars + 8u * s; };                         // local loads landed
-    auto empty_bar = [&](int s) { return bars + 8u * (kBatchStages + s); };       // UMMAs done with the stage (both CTAs)
-    auto ready_bar = [&](int s) { return bars + 8u * (2 * kBatchStages + s); };   // leader only: both CTAs' stage landed
-    const uint32_t tfull_bar = bars + 8u * (3 * kBatchStages);                    // accumulators complete
-    const uint32_t tempty_bar = bars + 8u * (3 * kBatchStages + 1);               // leader only: both epilogues drained
-    const uint32_t tmem_slot = bars + 8u * (3 * kBatchStages + 2);
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-        out_stage_ptr + 2 * kBatchOutStageBytes + 8 * (3 * kBatchStages + 2));
+    uint8_t* const out_stage_ptr = base_ptr + kStages * Cfg::kStageBytes;
+    const uint32_t bars = base + kStages * Cfg::kStageBytes + 2 * kBatchOutStageBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto ready_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    const uint32_t tfull_bar = bars + 8u * (3 * kStages);
+    const uint32_t tempty_bar = bars + 8u * (3 * kStages + 1);
+    const uint32_t tmem_slot = bars + 8u * (3 * kStages + 2);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(out_stage_ptr + 2 * kBatchOutStageBytes + 8 * (3 * kStages + 2));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -78,13 +90,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
     const uint32_t num_clusters = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kBatchStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
             ptx::mbar_init(ready_bar(s), 2);
         }
         ptx::mbar_init(tfull_bar, 1);
-        ptx::mbar_init(tempty_bar, 256);
+        ptx::mbar_init(tempty_bar, 8);
         ptx::fence_mbar_init();
     }
     if (warp == 5) ptx::tmem_alloc_2cta(tmem_slot, 512);
@@ -114,20 +126,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
                     q[i] = p.qd[qi < p.num_queries ? qi : p.num_queries - 1];
                 }
                 for (int c = 0; c < kChunks; ++c) {
-                    ptx::mbar_wait_cluster(empty_bar(stage), phase ^ 1u, p.error, kWbProducer);
-                    const uint32_t sbase = base + stage * kBatchStageBytes;
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWbProducer);
+                    const uint32_t sbase = base + stage * Cfg::kStageBytes;
                     const uint32_t fb = full_bar(stage);
-                    ptx::mbar_arrive_expect_tx(fb, SIGNED_Q ? kShareChunkBytes + kBatchBBytes : kBatchStageBytes);
-                    ptx::bulk_g2s(sbase + kBatchOffAlo, sh + (size_t)c * kShareChunkBytes, kShareChunkBytes, fb);
+                    ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                    ptx::bulk_g2s(sbase + Cfg::kOffAlo, sh + (size_t)c * kShareChunkBytes, kShareChunkBytes, fb);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        ptx::bulk_g2s_hint(sbase + kBatchOffBlo + i * kQTileBytes, q[i] + (size_t)c * kQdChunkBytes,
+                        ptx::bulk_g2s_hint(sbase + Cfg::kOffBlo + i * kQTileBytes, q[i] + (size_t)c * kQdChunkBytes,
                                            kQTileBytes, fb, pol_keep);
                         if (!SIGNED_Q)
-                            ptx::bulk_g2s_hint(sbase + kBatchOffBhi + i * kQTileBytes,
+                            ptx::bulk_g2s_hint(sbase + Cfg::kOffBhi + i * kQTileBytes,
                                                q[i] + (size_t)c * kQdChunkBytes + kQTileBytes, kQTileBytes, fb, pol_keep);
                     }
-                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -141,27 +153,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
             uint32_t it = 0;
             for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 if (rank == 0) {
-                    ptx::mbar_wait_cluster(tempty_bar, (it & 1u) ^ 1u, p.error, kWbTmemEmpty);
+                    ptx::mbar_wait(tempty_bar, (it & 1u) ^ 1u, p.error, kWbTmemEmpty);
                     ptx::tc_fence_after();
                 }
                 for (int c = 0; c < kChunks; ++c) {
                     ptx::mbar_wait(full_bar(stage), phase, p.error, kWbFull);
-                    ptx::mbar_arrive_cluster(ptx::mapa(ready_bar(stage), 0));      // tell the leader this half landed
+                    ptx::mbar_arrive_cluster(ptx::mapa(ready_bar(stage), 0));                // tell the leader this half landed
                     if (rank == 0) {
-                        ptx::mbar_wait_cluster(ready_bar(stage), phase, p.error, kWbReady);
+                        ptx::mbar_wait(ready_bar(stage), phase, p.error, kWbReady);
                         ptx::tc_fence_after();
-                        const uint32_t sbase = base + stage * kBatchStageBytes;
+                        const uint32_t sbase = base + stage * Cfg::kStageBytes;
 #pragma unroll
                         for (int k = 0; k < kChunkK / 32; ++k) {
                             const uint32_t acc = (c | k) ? 1u : 0u;
-                            const uint64_t alo = ptx::umma_desc_sw128(sbase + kBatchOffAlo + 32 * k);
-                            const uint64_t ahi = ptx::umma_desc_sw128(sbase + kBatchOffAhi + 32 * k);
-                            const uint64_t blo = ptx::umma_desc_sw128(sbase + kBatchOffBlo + 32 * k);
+                            const uint64_t alo = ptx::umma_desc_sw128(sbase + Cfg::kOffAlo + 32 * k);
+                            const uint64_t ahi = ptx::umma_desc_sw128(sbase + Cfg::kOffAhi + 32 * k);
+                            const uint64_t blo = ptx::umma_desc_sw128(sbase + Cfg::kOffBlo + 32 * k);
                             if (SIGNED_Q) {
                                 ptx::umma_i8_2cta(tmem_base + 0, alo, blo, kIdescS, acc);
                                 ptx::umma_i8_2cta(tmem_base + 256, ahi, blo, kIdescS, acc);
                             } else {
-                                const uint64_t bhi = ptx::umma_desc_sw128(sbase + kBatchOffBhi + 32 * k);
+                                const uint64_t bhi = ptx::umma_desc_sw128(sbase + Cfg::kOffBhi + 32 * k);
                                 ptx::umma_i8_2cta(tmem_base + 0, alo, blo, kIdescU, acc);
                                 ptx::umma_i8_2cta(tmem_base + 256, alo, bhi, kIdescU, acc);
                                 ptx::umma_i8_2cta(tmem_base + 256, ahi, blo, kIdescU, 1u);
@@ -170,7 +182,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
                         ptx::umma_commit_2cta(empty_bar(stage), 3);
                         if (c == kChunks - 1) ptx::umma_commit_2cta(tfull_bar, 3);
                     }
-                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -183,7 +195,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
         for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
             const uint32_t pair = p.pair_begin + t / num_groups;
             const uint32_t group = t % num_groups;
-            ptx::mbar_wait_cluster(tfull_bar, it & 1u, p.error, kWbEpilogue);
+            ptx::mbar_wait(tfull_bar, it & 1u, p.error, kWbEpilogue);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
             const int64_t trow0 = ((int64_t)2 * pair + rank) * kTileRows;
@@ -199,9 +211,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
                 ptx::tmem_ld32(taddr + 256 + 32 * g, b);
                 ptx::tmem_wait_ld();
                 if (g == kBatchQTile - 1) {
-                    // all accumulator columns of this CTA have been read: let the leader start the next tile
+                    // every accumulator column of this warp's lanes has been read: one arrive per warp lets the
+                    // leader start the next tile's UMMAs while the last query is still being written out
                     ptx::tc_fence_before();
-                    ptx::mbar_arrive_cluster(tempty_leader);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
                 }
                 if (qi < p.num_queries) {             // uniform over the CTA
                     uint8_t* outq = reinterpret_cast<uint8_t*>(p.out + (size_t)qi * rows_out * IRIS_ROTATIONS);
@@ -211,11 +225,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
 #pragma unroll
                     for (int j = 0; j < IRIS_ROTATIONS; ++j)
                         *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)(a[j] + (b[j] << 8));
+                    // staging buffers alternate per query: a thread can only write buffer (g&1) again after
+                    // passing the barrier of query g+1, which every thread reaches after its copy of query g.
                     ptx::named_bar_sync(1, 128);
                     copy_out_rows(stage_buf, outq + tile_off - shift, (int)shift + r0 * kOutRowBytes,
                                   (int)shift + r1 * kOutRowBytes, row);
-                    // staging buffers alternate per query: a thread can only write buffer (g&1) again after
-                    // passing the barrier of query g+1, which every thread reaches after its copy of query g.
                 }
             }
         }
@@ -229,13 +243,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
 
 template <bool SIGNED_Q>
 static cudaError_t launch_batch_t(const BatchParams& p, int num_sms, cudaStream_t stream) {
+    using Cfg = BatchCfg<SIGNED_Q>;
     static bool configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && !configured[dev]) {
         e = cudaFuncSetAttribute(batch_distances_kernel<SIGNED_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kBatchSmemBytes);
+                                 Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -244,7 +259,7 @@ static cudaError_t launch_batch_t(const BatchParams& p, int num_sms, cudaStream_
     if (tiles == 0) return cudaSuccess;
     uint32_t clusters = (uint32_t)num_sms / 2;
     if (tiles < clusters) clusters = tiles;
-    batch_distances_kernel<SIGNED_Q><<<2 * clusters, kBatchThreads, kBatchSmemBytes, stream>>>(p);
+    batch_distances_kernel<SIGNED_Q><<<2 * clusters, kBatchThreads, Cfg::kSmemBytes, stream>>>(p);
     count_launch_external();
     return cudaGetLastError();
 }

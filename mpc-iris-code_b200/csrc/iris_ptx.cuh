@@ -169,7 +169,9 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default .release.cta semantics: a bare SYNCS.ARRIVE.  (.release.cluster costs MEMBAR.ALL.GPU + ERRBAR per
+    // arrive and is not needed here: only async-proxy data -- TMA writes, UMMA reads, TMEM -- crosses CTAs.)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;

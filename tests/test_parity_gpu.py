@@ -362,3 +362,54 @@ def test_full_size_scan_properties(iris):
         db.synchronize()
         db.check_distances_simt(qu, 0, n, cd)
         assert torch.equal(dd, cd)
+
+
+# ----------------------------------------------------------------------------------- batched queries (config 4)
+@pytest.mark.parametrize("kind,nq", [("ternary", 8), ("uniform", 8), ("ternary", 5), ("mixed", 20), ("ternary", 1), ("uniform", 13)])
+def test_distances_batch_matches_per_engine_and_oracle(iris, small, kind, nq):
+    """iris_distances_batch_resident (2-CTA tcgen05 GEMM) == batch_process per engine == oracle.
+    Ternary batches take the signed two-product path, any non-s8 query forces the three-product path."""
+    db, shares, _ = small
+    qs = []
+    for i in range(nq):
+        tern = kind == "ternary" or (kind == "mixed" and i % 3)
+        qs.append(ternary_query(700 + i)[0] if tern else uniform_query(800 + i))
+    engines = [iris.DistanceEngine(q) for q in qs]
+    exp = np.stack([O.distance_batch(q, shares, threads=8) for q in qs])
+    for rb, re in ((0, 1000), (3, 997), (256, 512), (511, 513)):
+        out = np.full((nq, re - rb, 31), 0x5A5A, np.uint16)
+        iris.distances_batch(engines, db, rb, re, out)
+        assert np.array_equal(out, exp[:, rb:re]), (kind, nq, rb, re)
+    single = np.zeros((1000, 31), np.uint16)
+    engines[-1].batch_process(single, db)
+    assert np.array_equal(single, exp[-1])
+
+
+def test_distances_batch_device_output_and_s8_edge_values(iris, small):
+    import torch
+
+    db, shares, _ = small
+    # values at the edge of the signed-byte fast path: 0x7F / 0xFF80 are s8, 0x80 / 0xFF7F are not
+    q_s8 = np.tile(np.array([0x7F, 0xFF80, 0, 1, 0xFFFF], np.uint16), O.BITS // 5)
+    q_u = q_s8.copy()
+    q_u[7] = 0x80
+    q_v = q_s8.copy()
+    q_v[9] = 0xFF7F
+    for qs in ([q_s8] * 3, [q_s8, q_u], [q_v]):
+        engines = [iris.DistanceEngine(q) for q in qs]
+        out = torch.zeros((len(qs), 1000, 31), dtype=torch.int16, device="cuda")
+        iris.distances_batch(engines, db, 0, 1000, out)
+        db.synchronize()
+        got = out.cpu().numpy().view(np.uint16)
+        for i, q in enumerate(qs):
+            assert np.array_equal(got[i], O.distance_batch(q, shares, threads=8))
+
+
+def test_distances_batch_errors(iris, small):
+    db, _, _ = small
+    e = iris.DistanceEngine(uniform_query(900))
+    with pytest.raises(iris.IrisError):
+        iris.distances_batch([e], db, 0, 2000, np.zeros((1, 2000, 31), np.uint16))     # beyond loaded rows
+    with pytest.raises(ValueError):
+        iris.distances_batch([e, e], db, 0, 10, np.zeros((1, 10, 31), np.uint16))      # out too small
+    iris.distances_batch([e], db, 5, 5, np.zeros((1, 0, 31), np.uint16))               # empty range is fine
