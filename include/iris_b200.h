@@ -121,6 +121,8 @@ int iris_match_resident(iris_distance_engine *de, iris_masks_engine *me, iris_db
  * out = [num_queries][row_end-row_begin][31] u16, host or device memory. ---- */
 int iris_distances_batch_resident(iris_distance_engine *const *engines, uint32_t num_queries, iris_db *db,
                                   uint64_t row_begin, uint64_t row_end, uint16_t *out);
+int iris_denominators_batch_resident(iris_masks_engine *const *engines, uint32_t num_queries, iris_db *db,
+                                     uint64_t row_begin, uint64_t row_end, uint16_t *out);
 
 /* ---- single-pair wrappers: src/lib.rs:82-87 and :89-94 ---- */
 int iris_distances(int device, const uint16_t query[IRIS_BITS], const uint16_t entry[IRIS_BITS],

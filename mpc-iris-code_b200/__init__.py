@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     IrisError,
     MasksEngine,
     denominators,
+    denominators_batch,
     device_count,
     distances,
     distances_batch,

@@ -74,6 +74,7 @@ def lib():
         "iris_masks_engine_batch_process_resident": [vp, vp, u64, vp, u64, u64],
         "iris_match_resident": [vp, vp, vp, u64, u64, vp, vp],
         "iris_distances_batch_resident": [vp, u32, vp, u64, u64, vp],
+        "iris_denominators_batch_resident": [vp, u32, vp, u64, u64, vp],
         "iris_distances": [i32, vp, vp, vp],
         "iris_denominators": [i32, vp, vp, vp],
         "iris_check_distances_simt": [vp, vp, u64, u64, vp],
@@ -340,6 +341,14 @@ def distances_batch(engines, db: Database, row_begin: int, row_end: int, out) ->
     n = len(engines) * (row_end - row_begin) * ROTATIONS
     arr = (ctypes.c_void_p * len(engines))(*[e._h.value for e in engines])
     _check(lib().iris_distances_batch_resident(arr, len(engines), db._h, row_begin, row_end, _ptr(out, np.uint16, n, "out")))
+
+
+def denominators_batch(engines, db: Database, row_begin: int, row_end: int, out) -> None:
+    """All `engines` (MasksEngine list) against rows [row_begin,row_end) as one tensor-core GEMM;
+    out = [len(engines)][rows][31] u16."""
+    n = len(engines) * (row_end - row_begin) * ROTATIONS
+    arr = (ctypes.c_void_p * len(engines))(*[e._h.value for e in engines])
+    _check(lib().iris_denominators_batch_resident(arr, len(engines), db._h, row_begin, row_end, _ptr(out, np.uint16, n, "out")))
 
 
 def raw_accumulators(distance_engine, masks_engine, db: Database, row_begin: int, row_end: int) -> np.ndarray:

@@ -709,6 +709,55 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
     return rc;
 }
 
+extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engines, uint32_t num_queries, iris_db* db,
+                                                uint64_t row_begin, uint64_t row_end, uint16_t* out) {
+    if (!engines || !db) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (num_queries == 0) return IRIS_OK;
+    if (row_begin > row_end) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    if (!db->d_masks) return fail(IRIS_ERR_STATE, "shard holds no masks");
+    if (row_end > db->n_masks) return fail(IRIS_ERR_INVALID, "row_end beyond loaded masks");
+    if (row_begin == row_end) return IRIS_OK;
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    for (uint32_t i = 0; i < num_queries; ++i) {
+        if (!engines[i]) return fail(IRIS_ERR_INVALID, "engine %u is NULL", i);
+        if (engines[i]->device != db->device) return fail(IRIS_ERR_INVALID, "engine %u lives on another device", i);
+    }
+    DeviceGuard g(db->device);
+    const uint64_t rows = row_end - row_begin;
+    const bool out_dev = is_device_pointer(out);
+    uint16_t* d_out = out;
+    const size_t out_bytes = (size_t)num_queries * rows * kOutRowBytes;
+    if (!out_dev) CK(cudaMalloc(&d_out, out_bytes + 64));
+    auto body = [&]() -> int {
+        for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxBatchQueries) {
+            const uint32_t nq = std::min<uint32_t>(kMaxBatchQueries, num_queries - q0);
+            BatchMaskParams p{};
+            p.masks = db->d_masks;
+            for (uint32_t i = 0; i < nq; ++i) p.qm[i] = engines[q0 + i]->d_qm;
+            p.out = d_out + (size_t)q0 * rows * IRIS_ROTATIONS;
+            p.row_begin = row_begin;
+            p.row_end = row_end;
+            p.pair_begin = (uint32_t)(row_begin / (2 * kTileRows));
+            p.pair_end = (uint32_t)((row_end + 2 * kTileRows - 1) / (2 * kTileRows));
+            p.num_queries = nq;
+            p.error = db->d_error;
+            CK(launch_batch_denominators(p, db->num_sms, db->stream));
+        }
+        if (!out_dev) {
+            CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, db->stream));
+            CK(cudaStreamSynchronize(db->stream));
+            return check_error_flag(db);
+        }
+        return IRIS_OK;
+    };
+    int rc = body();
+    if (!out_dev) {
+        cudaStreamSynchronize(db->stream);
+        cudaFree(d_out);
+    }
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------ per-pair arch entry points
 template <typename T, typename F>
 static int dot_pair(int device, const T* a, const T* b, size_t bytes, uint16_t* out, F launch) {

@@ -269,4 +269,231 @@ cudaError_t launch_batch_distances(const BatchParams& p, bool signed_queries, in
     return signed_queries ? launch_batch_t<true>(p, num_sms, stream) : launch_batch_t<false>(p, num_sms, stream);
 }
 
+// =====================================================================================
+// batched denominators: popcount(rot(qmask_g, j-15) & dbmask_i) for 16 query masks per cluster tile.
+// A = database mask bits expanded to bytes inside the SM (one LOP per 4 bytes, value 2^t, see
+// iris_kernels.cu), B = prepared mask operand images (value 2^(7-t)), D >> 7 = popcount.
+// 16 queries x 32 rotations = 512 s32 accumulator columns = two N=256 UMMAs per K step.
+// =====================================================================================
+constexpr int kMaskQTile = 16;
+constexpr int kMaskStages = 4;
+constexpr int kMaskOffAmx = 0;                                  // 16 KiB expanded operand (written by the SM)
+constexpr int kMaskOffB = kPlaneTileBytes;                      // 8 query tiles of 4 KiB (this CTA's half)
+constexpr int kMaskOffPk = kPlaneTileBytes + 8 * kQTileBytes;   // 2 KiB packed mask bytes
+constexpr int kMaskStageBytes = kMaskOffPk + kMaskChunkBytes;   // 50 KiB
+constexpr int kMaskSmemBytes = 1024 + kMaskStages * kMaskStageBytes + 2 * kBatchOutStageBytes + 512;
+constexpr int kMaskThreads = 320;                               // + warps 6..9 expanders
+static_assert(kMaskStageBytes % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+static_assert(kMaskSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
+
+enum MaskWatchdog { kWmProducer = 301, kWmFull = 302, kWmExp = 303, kWmReady = 304, kWmTmemEmpty = 305, kWmEpilogue = 306, kWmExpander = 307 };
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMaskThreads, 1)
+    batch_denominators_kernel(const BatchMaskParams p) {
+    constexpr int kStages = kMaskStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* const base_ptr = smem_raw + (base - raw_addr);
+    uint8_t* const out_stage_ptr = base_ptr + kStages * kMaskStageBytes;
+    const uint32_t bars = base + kStages * kMaskStageBytes + 2 * kBatchOutStageBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto ready_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto expd_bar = [&](int s) { return bars + 8u * (3 * kStages + s); };
+    const uint32_t tfull_bar = bars + 8u * (4 * kStages);
+    const uint32_t tempty_bar = bars + 8u * (4 * kStages + 1);
+    const uint32_t tmem_slot = bars + 8u * (4 * kStages + 2);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(out_stage_ptr + 2 * kBatchOutStageBytes + 8 * (4 * kStages + 2));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const uint32_t cluster_id = blockIdx.x >> 1;
+    const uint32_t num_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+            ptx::mbar_init(ready_bar(s), 2);
+            ptx::mbar_init(expd_bar(s), 128);
+        }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::mbar_init(tempty_bar, 8);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 5) ptx::tmem_alloc_2cta(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const uint32_t num_groups = (p.num_queries + kMaskQTile - 1) / kMaskQTile;
+    const uint32_t num_tiles = (p.pair_end - p.pair_begin) * num_groups;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t pol_keep = ptx::policy_evict_last();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+                const uint32_t pair = p.pair_begin + t / num_groups;
+                const uint32_t group = t % num_groups;
+                const uint8_t* mk = p.masks + (size_t)(2 * pair + rank) * kMaskTileBytes;
+                // this CTA's half of both N=256 operands: queries {0..3, 8..11} (rank 0) or {4..7, 12..15} (rank 1)
+                const uint8_t* q[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t qi = group * kMaskQTile + (i < 4 ? 4 * rank + i : 8 + 4 * rank + (i - 4));
+                    q[i] = p.qm[qi < p.num_queries ? qi : p.num_queries - 1];
+                }
+                for (int c = 0; c < kChunks; ++c) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWmProducer);
+                    const uint32_t sbase = base + stage * kMaskStageBytes;
+                    const uint32_t fb = full_bar(stage);
+                    ptx::mbar_arrive_expect_tx(fb, 8 * kQTileBytes + kMaskChunkBytes);
+                    ptx::bulk_g2s(sbase + kMaskOffPk, mk + (size_t)c * kMaskChunkBytes, kMaskChunkBytes, fb);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        ptx::bulk_g2s_hint(sbase + kMaskOffB + i * kQTileBytes, q[i] + (size_t)c * kQmChunkBytes, kQTileBytes,
+                                           fb, pol_keep);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ relay (both CTAs) + UMMA issue (leader)
+        if (lane == 0) {
+            constexpr uint32_t kIdesc = ptx::umma_idesc_i8_m256(256, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                if (rank == 0) {
+                    ptx::mbar_wait(tempty_bar, (it & 1u) ^ 1u, p.error, kWmTmemEmpty);
+                    ptx::tc_fence_after();
+                }
+                for (int c = 0; c < kChunks; ++c) {
+                    ptx::mbar_wait(full_bar(stage), phase, p.error, kWmFull);        // query operand landed
+                    ptx::mbar_wait(expd_bar(stage), phase, p.error, kWmExp);         // mask operand expanded
+                    ptx::mbar_arrive_cluster(ptx::mapa(ready_bar(stage), 0));
+                    if (rank == 0) {
+                        ptx::mbar_wait(ready_bar(stage), phase, p.error, kWmReady);
+                        ptx::tc_fence_after();
+                        const uint32_t sbase = base + stage * kMaskStageBytes;
+#pragma unroll
+                        for (int k = 0; k < kChunkK / 32; ++k) {
+                            const uint32_t acc = (c | k) ? 1u : 0u;
+                            const uint64_t a = ptx::umma_desc_sw128(sbase + kMaskOffAmx + 32 * k);
+                            ptx::umma_i8_2cta(tmem_base + 0, a, ptx::umma_desc_sw128(sbase + kMaskOffB + 32 * k), kIdesc, acc);
+                            ptx::umma_i8_2cta(tmem_base + 256, a,
+                                              ptx::umma_desc_sw128(sbase + kMaskOffB + 4 * kQTileBytes + 32 * k), kIdesc, acc);
+                        }
+                        ptx::umma_commit_2cta(empty_bar(stage), 3);
+                        if (c == kChunks - 1) ptx::umma_commit_2cta(tfull_bar, 3);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 6) {
+        // ------------------------------------------------------------------ mask bit -> byte expanders (own 128 rows)
+        const int row = threadIdx.x - 6 * 32;
+        const uint32_t sw = row & 7;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+            for (int c = 0; c < kChunks; ++c) {
+                ptx::mbar_wait(full_bar(stage), phase, p.error, kWmExpander);
+                uint8_t* sptr = base_ptr + stage * kMaskStageBytes;
+                const uint4 x = *reinterpret_cast<const uint4*>(sptr + kMaskOffPk + row * 16);
+                uint8_t* dst = sptr + kMaskOffAmx + row * 128;
+                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t v = xs[w];
+                    uint4 lo4 = make_uint4(v & 0x01010101u, v & 0x02020202u, v & 0x04040404u, v & 0x08080808u);
+                    uint4 hi4 = make_uint4(v & 0x10101010u, v & 0x20202020u, v & 0x40404040u, v & 0x80808080u);
+                    *reinterpret_cast<uint4*>(dst + (((2 * w) ^ sw) << 4)) = lo4;
+                    *reinterpret_cast<uint4*>(dst + (((2 * w + 1) ^ sw) << 4)) = hi4;
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(expd_bar(stage));
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 0..3 of each CTA)
+        const int row = threadIdx.x;
+        const uint32_t tempty_leader = ptx::mapa(tempty_bar, 0);
+        const uint64_t rows_out = p.row_end - p.row_begin;
+        uint32_t it = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            const uint32_t pair = p.pair_begin + t / num_groups;
+            const uint32_t group = t % num_groups;
+            ptx::mbar_wait(tfull_bar, it & 1u, p.error, kWmEpilogue);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const int64_t trow0 = ((int64_t)2 * pair + rank) * kTileRows;
+            int64_t lo = (int64_t)p.row_begin - trow0, hi = (int64_t)p.row_end - trow0;
+            const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
+            const int r1 = (int)(hi < 0 ? 0 : (hi > kTileRows ? kTileRows : hi));
+            const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
+#pragma unroll 1
+            for (int g = 0; g < kMaskQTile; ++g) {
+                const uint32_t qi = group * kMaskQTile + g;
+                uint32_t a[32];
+                ptx::tmem_ld32(taddr + 32 * g, a);
+                ptx::tmem_wait_ld();
+                if (g == kMaskQTile - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
+                }
+                if (qi < p.num_queries) {
+                    uint8_t* outq = reinterpret_cast<uint8_t*>(p.out + (size_t)qi * rows_out * IRIS_ROTATIONS);
+                    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(outq) + tile_off) & 15);
+                    uint8_t* stage_buf = out_stage_ptr + (g & 1) * kBatchOutStageBytes;
+                    uint8_t* st = stage_buf + shift + row * kOutRowBytes;
+#pragma unroll
+                    for (int j = 0; j < IRIS_ROTATIONS; ++j) *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)(a[j] >> 7);
+                    ptx::named_bar_sync(1, 128);
+                    copy_out_rows(stage_buf, outq + tile_off - shift, (int)shift + r0 * kOutRowBytes,
+                                  (int)shift + r1 * kOutRowBytes, row);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 5) ptx::tmem_dealloc_2cta(tmem_base, 512);
+}
+
+cudaError_t launch_batch_denominators(const BatchMaskParams& p, int num_sms, cudaStream_t stream) {
+    if (p.num_queries == 0 || p.num_queries > kMaxBatchQueries) return cudaErrorInvalidValue;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && !configured[dev]) {
+        e = cudaFuncSetAttribute(batch_denominators_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const uint32_t num_groups = (p.num_queries + kMaskQTile - 1) / kMaskQTile;
+    const uint32_t tiles = (p.pair_end - p.pair_begin) * num_groups;
+    if (tiles == 0) return cudaSuccess;
+    uint32_t clusters = (uint32_t)num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    batch_denominators_kernel<<<2 * clusters, kMaskThreads, kMaskSmemBytes, stream>>>(p);
+    count_launch_external();
+    return cudaGetLastError();
+}
+
 }  // namespace iris

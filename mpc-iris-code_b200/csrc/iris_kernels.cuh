@@ -66,6 +66,18 @@ struct BatchParams {
 };
 cudaError_t launch_batch_distances(const BatchParams& p, bool signed_queries, int num_sms, cudaStream_t stream);
 
+// Batched denominators: same shape for prepared mask operand images.
+struct BatchMaskParams {
+    const uint8_t* masks;
+    const uint8_t* qm[kMaxBatchQueries];
+    uint16_t* out;
+    uint64_t row_begin, row_end;
+    uint32_t pair_begin, pair_end;
+    uint32_t num_queries;
+    int* error;
+};
+cudaError_t launch_batch_denominators(const BatchMaskParams& p, int num_sms, cudaStream_t stream);
+
 // Number of kernels launched by this library since load (bench.py's gpu_launches).
 uint64_t launch_count();
 

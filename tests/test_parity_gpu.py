@@ -413,3 +413,20 @@ def test_distances_batch_errors(iris, small):
     with pytest.raises(ValueError):
         iris.distances_batch([e, e], db, 0, 10, np.zeros((1, 10, 31), np.uint16))      # out too small
     iris.distances_batch([e], db, 5, 5, np.zeros((1, 0, 31), np.uint16))               # empty range is fine
+
+
+@pytest.mark.parametrize("nq", [16, 1, 5, 37])
+def test_denominators_batch_matches_per_engine_and_oracle(iris, small, nq):
+    """iris_denominators_batch_resident (2-CTA tcgen05 GEMM over in-SM expanded mask bits) == oracle."""
+    db, _, masks = small
+    qms = [O.gen_mask_rows(1000 + i, 1, 1)[0] for i in range(nq)]
+    qms[0] = np.full(O.LIMBS, 2**64 - 1, np.uint64)          # all-ones mask: denominators = popcount of the row
+    engines = [iris.MasksEngine(q) for q in qms]
+    exp = np.stack([O.masks_batch(q, masks, threads=8) for q in qms])
+    for rb, re in ((0, 1000), (3, 997), (256, 512), (511, 513)):
+        out = np.full((nq, re - rb, 31), 0x5A5A, np.uint16)
+        iris.denominators_batch(engines, db, rb, re, out)
+        assert np.array_equal(out, exp[:, rb:re]), (nq, rb, re)
+    single = np.zeros((1000, 31), np.uint16)
+    engines[-1].batch_process(single, db)
+    assert np.array_equal(single, exp[-1])

@@ -54,7 +54,54 @@ def correctness():
             ok_all = False
             print(f"[FAIL] batch {name}: {e}", flush=True)
     db.close()
+    # batched denominators
+    masks = O.gen_mask_rows(SEED, 0, n, threads=8)
+    dbm = iris.Database(n, shares=False)
+    dbm.append_masks(masks)
+    for nqm in (16, 5, 37):
+        try:
+            qms = [O.gen_mask_rows(900 + i, 1, 1)[0] for i in range(nqm)]
+            engines = [iris.MasksEngine(q) for q in qms]
+            exp = np.stack([O.masks_batch(q, masks, threads=8) for q in qms])
+            for rb, re in ((0, n), (3, 997), (256, 512), (300, 301)):
+                out = np.zeros((nqm, re - rb, 31), np.uint16)
+                iris.denominators_batch(engines, dbm, rb, re, out)
+                ok = np.array_equal(out, exp[:, rb:re])
+                ok_all &= ok
+                print(f"[{'PASS' if ok else 'FAIL'}] batch denominators x{nqm} rows[{rb}:{re}] {'' if ok else describe(out, exp[:, rb:re])}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            traceback.print_exc()
+            ok_all = False
+            print(f"[FAIL] batch denominators x{nqm}: {e}", flush=True)
+    dbm.close()
     return ok_all
+
+
+def timing_masks(n, nq):
+    stream = torch.cuda.Stream()
+    db = iris.Database(n, shares=False)
+    db.generate(SEED, 0, n)
+    db.set_stream(stream.cuda_stream)
+    out = torch.empty((nq, n, 31), dtype=torch.int16, device="cuda")
+    qms = [O.gen_mask_rows(950 + i, 1, 1)[0] for i in range(nq)]
+    engines = [iris.MasksEngine(q) for q in qms]
+    for _ in range(2):
+        iris.denominators_batch(engines, db, 0, n, out)
+    db.synchronize()
+    iters = 5
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
+    for _ in range(iters):
+        iris.denominators_batch(engines, db, 0, n, out)
+    e.record(stream)
+    db.synchronize()
+    ms = s.elapsed_time(e) / iters
+    print(f"denominators batch: n={n} Q={nq} {ms:.3f} ms -> {n * nq / (ms * 1e-3):.3e} cmp/s; issued "
+          f"{2 * n * nq * 32 * 12800 / (ms * 1e-3) / 1e15:.3f} Pop/s", flush=True)
+    got = out.cpu().numpy().view(np.uint16)
+    ok = all(np.array_equal(got[qi, i], O.masks_batch(qms[qi], O.gen_mask_rows(SEED, i, 1))[0]) for qi in (0, nq - 1) for i in (0, 255, 256, n - 1))
+    print("  sampled parity:", ok, flush=True)
+    db.close()
 
 
 def timing(n, nq):
@@ -111,5 +158,6 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
     nq = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     if ok or "--force-timing" in sys.argv:
+        timing_masks(n, nq)
         timing(n, nq)
     sys.exit(0 if ok else 1)
