@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (denominators only, batched GEMM)")
     return ap.parse_args()
 
 
@@ -202,6 +203,77 @@ def nvml_index(local_rank: int) -> int:
     return local_rank
 
 
+# ----------------------------------------------------------------------------------- secondary configs
+def _time_ms(stream, fn, sync, warmup=2, iters=5):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    sync()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
+    for _ in range(iters):
+        fn()
+    e.record(stream)
+    sync()
+    return s.elapsed_time(e) / iters
+
+
+def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
+    """BASELINE configs[2] (denominators only) and configs[3] (64 queries as a dense int8 GEMM) on the same shard,
+    kernel-only, reported next to the headline so the driver's own run carries them."""
+    import torch
+
+    import oracle as O
+
+    out = {}
+    ms = _time_ms(stream, lambda: iris.match(None, me, db, 0, rows, None, d_den), db.synchronize)
+    out["denominators_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
+                                   "algorithmic_GBps": rows * 1662 / (ms * 1e-3) / 1e9,
+                                   "note": "issue/latency bound, not HBM bound (DESIGN.md 5.1)"}
+    ms = _time_ms(stream, lambda: iris.match(de, None, db, 0, rows, d_dist, None), db.synchronize)
+    out["distances_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
+                                "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9}
+    # int8 library GEMM on this box: the measured tensor-core denominator
+    a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
+    b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
+    for _ in range(3):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        torch._int_mm(a, b)
+    e.record()
+    torch.cuda.synchronize()
+    lib_pops = 2 * 8192**3 / (s.elapsed_time(e) / 20 * 1e-3) / 1e15
+    del a, b
+    nq = 64
+    tern = [O.np_encode(O.gen_mask_rows(7000 + i, 0, 1)[0], O.gen_mask_rows(7000 + i, 1, 1)[0]) for i in range(nq)]
+    unif = [O.gen_share_rows(8000 + i, 0, 1)[0] for i in range(nq)]
+    qms = [O.gen_mask_rows(7000 + i, 1, 1)[0] for i in range(nq)]
+    big = torch.empty((nq, rows, 31), dtype=torch.int16, device="cuda")
+    res = {"queries": nq, "rows": rows, "int8_library_gemm_Pops": lib_pops, "int8_nominal_Pops": 4.5}
+    for name, qs, prods in (("ternary", tern, 2), ("uniform_u16", unif, 3)):
+        eng = [iris.DistanceEngine(x) for x in qs]
+        ms = _time_ms(stream, lambda: iris.distances_batch(eng, db, 0, rows, big), db.synchronize, warmup=1, iters=3)
+        useful = 2 * rows * nq * 31 * 12800 * prods / (ms * 1e-3) / 1e15
+        res[f"distances_{name}"] = {"ms": ms, "comparisons_per_s": rows * nq / (ms * 1e-3), "limb_products": prods,
+                                    "useful_int8_Pops": useful, "frac_of_nominal": useful / 4.5,
+                                    "frac_of_library_gemm": useful / lib_pops}
+        for x in eng:
+            x.close()
+    eng = [iris.MasksEngine(x) for x in qms]
+    ms = _time_ms(stream, lambda: iris.denominators_batch(eng, db, 0, rows, big), db.synchronize, warmup=1, iters=3)
+    useful = 2 * rows * nq * 31 * 12800 / (ms * 1e-3) / 1e15
+    res["denominators"] = {"ms": ms, "comparisons_per_s": rows * nq / (ms * 1e-3), "useful_int8_Pops": useful,
+                           "frac_of_nominal": useful / 4.5, "frac_of_library_gemm": useful / lib_pops}
+    both = res["distances_ternary"]["ms"] + res["denominators"]["ms"]
+    res["distances_plus_denominators_ternary"] = {"ms": both, "comparisons_per_s": rows * nq / (both * 1e-3)}
+    out["batched_64q_int8_gemm"] = res
+    return out
+
+
 # ----------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
@@ -343,6 +415,11 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if world == 1 and not args.no_extras:
+        try:
+            line["extras"] = secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den)
+        except Exception as ex:  # noqa: BLE001
+            line["extras"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, q, qm)
     print(json.dumps(line), flush=True)
