@@ -77,6 +77,12 @@ int iris_db_len(const iris_db *db, uint64_t *n_shares, uint64_t *n_masks);
 /* Append rows given in the reference's flat-file layouts (host pointers). */
 int iris_db_append_shares(iris_db *db, const uint16_t *rows /* [n][12800] */, uint64_t n);
 int iris_db_append_masks(iris_db *db, const uint64_t *rows /* [n][200] */, uint64_t n);
+/* Append rows [first_row, first_row+n_rows) (n_rows = 0: to the end) of a file in the reference's on-disk
+ * formats: `mpc.share-i` = raw EncodedBits rows, `mpc.masks` = raw Bits rows (written by `prepare`,
+ * src/main.rs:337-371; mmapped at src/main.rs:386-400, 458-461).  A size that is not a whole number of rows
+ * is an error (the reference's try_cast_slice failure, src/main.rs:391-392). */
+int iris_db_load_shares_file(iris_db *db, const char *path, uint64_t first_row, uint64_t n_rows);
+int iris_db_load_masks_file(iris_db *db, const char *path, uint64_t first_row, uint64_t n_rows);
 /* Append n synthetic rows (uniform u16 shares and/or uniform mask bits, per `flags` of the
  * shard) produced on the device by a counter-based generator keyed by (seed, row id);
  * row ids are first_row_id, first_row_id+1, ...  (oracle/iris_oracle.c restates the generator). */
@@ -123,6 +129,20 @@ int iris_distances_batch_resident(iris_distance_engine *const *engines, uint32_t
                                   uint64_t row_begin, uint64_t row_end, uint16_t *out);
 int iris_denominators_batch_resident(iris_masks_engine *const *engines, uint32_t num_queries, iris_db *db,
                                      uint64_t row_begin, uint64_t row_end, uint16_t *out);
+
+/* ---- coordinator reduction on the device (src/main.rs:597-621 with decode_distance, src/lib.rs:97-107):
+ * numerator = wrapping sum of the parties' distance shares; distance = min over rotations of
+ * ((den - num) as u16 / 2) / den in f64 (NaN ignored); running min with `<` (first minimum wins;
+ * min_index = UINT64_MAX when nothing is below +inf).  Inputs are [n][31] u16 arrays, host or device;
+ * distances_out (optional, [n] f64) receives the per-row decoded distances.  Bit-identical to the CPU. ---- */
+int iris_combine_min(int device, const uint16_t *const *distance_shares, uint32_t parties,
+                     const uint16_t *denominators, uint64_t n, uint64_t index_base, double *distances_out,
+                     double *min_distance, uint64_t *min_index);
+/* Fused scan + reduction for a shard that holds the whole (1-share) encodings: both engines over rows
+ * [row_begin,row_end), decode and min/argmin on the device; only 16 bytes return to the host.  This is
+ * the per-shard step of the multi-GPU path (each rank reduces its rows, the pairs are all-gathered). */
+int iris_match_min_resident(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
+                            uint64_t row_end, uint64_t index_base, double *min_distance, uint64_t *min_index);
 
 /* ---- single-pair wrappers: src/lib.rs:82-87 and :89-94 ---- */
 int iris_distances(int device, const uint16_t query[IRIS_BITS], const uint16_t entry[IRIS_BITS],

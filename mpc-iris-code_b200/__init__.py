@@ -17,6 +17,8 @@ from .api import (  # noqa: F401
     DistanceEngine,
     IrisError,
     MasksEngine,
+    combine_min,
+    match_min,
     denominators,
     denominators_batch,
     device_count,

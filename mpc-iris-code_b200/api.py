@@ -60,6 +60,8 @@ def lib():
         "iris_db_append_shares": [vp, vp, u64],
         "iris_db_append_masks": [vp, vp, u64],
         "iris_db_generate": [vp, u64, u64, u64],
+        "iris_db_load_shares_file": [vp, ctypes.c_char_p, u64, u64],
+        "iris_db_load_masks_file": [vp, ctypes.c_char_p, u64, u64],
         "iris_db_read_shares": [vp, u64, u64, vp],
         "iris_db_read_masks": [vp, u64, u64, vp],
         "iris_db_set_stream": [vp, vp],
@@ -75,6 +77,8 @@ def lib():
         "iris_match_resident": [vp, vp, vp, u64, u64, vp, vp],
         "iris_distances_batch_resident": [vp, u32, vp, u64, u64, vp],
         "iris_denominators_batch_resident": [vp, u32, vp, u64, u64, vp],
+        "iris_combine_min": [i32, vp, u32, vp, u64, u64, vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
+        "iris_match_min_resident": [vp, vp, vp, u64, u64, u64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
         "iris_distances": [i32, vp, vp, vp],
         "iris_denominators": [i32, vp, vp, vp],
         "iris_check_distances_simt": [vp, vp, u64, u64, vp],
@@ -211,6 +215,14 @@ class Database:
         if n * LIMBS != _numel(rows):
             raise ValueError("masks must be [n][200] u64")
         _check(lib().iris_db_append_masks(self._h, _ptr(rows, np.uint64, n * LIMBS, "rows"), n))
+
+    def load_shares_file(self, path: str, first_row: int = 0, n_rows: int = 0) -> None:
+        """Append rows of a reference `mpc.share-i` file (raw EncodedBits rows, src/main.rs:355-371)."""
+        _check(lib().iris_db_load_shares_file(self._h, os.fsencode(path), first_row, n_rows))
+
+    def load_masks_file(self, path: str, first_row: int = 0, n_rows: int = 0) -> None:
+        """Append rows of a reference `mpc.masks` file (raw Bits rows, src/main.rs:341-367)."""
+        _check(lib().iris_db_load_masks_file(self._h, os.fsencode(path), first_row, n_rows))
 
     def generate(self, seed: int, first_row_id: int, n: int) -> None:
         _check(lib().iris_db_generate(self._h, seed, first_row_id, n))
@@ -349,6 +361,32 @@ def denominators_batch(engines, db: Database, row_begin: int, row_end: int, out)
     n = len(engines) * (row_end - row_begin) * ROTATIONS
     arr = (ctypes.c_void_p * len(engines))(*[e._h.value for e in engines])
     _check(lib().iris_denominators_batch_resident(arr, len(engines), db._h, row_begin, row_end, _ptr(out, np.uint16, n, "out")))
+
+
+def combine_min(distance_shares, denominators, index_base: int = 0, device: int = 0, want_distances: bool = False):
+    """Coordinator reduction (src/main.rs:597-621 + decode_distance src/lib.rs:97-107) on the device.
+    `distance_shares`: list of [n][31] u16 arrays (one per party), `denominators`: [n][31] u16.
+    Returns (min_distance, min_index) or (min_distance, min_index, distances[n]) ; min_index is -1 when no
+    distance is below +inf (the reference leaves usize::MAX)."""
+    n = _numel(denominators) // ROTATIONS
+    arr = (ctypes.c_void_p * len(distance_shares))(*[_ptr(s, np.uint16, n * ROTATIONS, "share") for s in distance_shares])
+    md, mi = ctypes.c_double(), ctypes.c_uint64()
+    dist = np.empty(n, np.float64) if want_distances else None
+    _check(lib().iris_combine_min(device, arr, len(distance_shares), _ptr(denominators, np.uint16, n * ROTATIONS, "denominators"),
+                                  n, index_base, dist.ctypes.data if want_distances else None,
+                                  ctypes.byref(md), ctypes.byref(mi)))
+    idx = -1 if mi.value == 2**64 - 1 else mi.value
+    return (md.value, idx, dist) if want_distances else (md.value, idx)
+
+
+def match_min(distance_engine: DistanceEngine, masks_engine: MasksEngine, db: Database, row_begin: int, row_end: int,
+              index_base: int = 0):
+    """Fused scan + decode + min/argmin on the device for a shard holding whole encodings; returns
+    (min_distance, global_row) with global_row = index_base + row, or -1 if nothing is below +inf."""
+    md, mi = ctypes.c_double(), ctypes.c_uint64()
+    _check(lib().iris_match_min_resident(distance_engine._h, masks_engine._h, db._h, row_begin, row_end, index_base,
+                                         ctypes.byref(md), ctypes.byref(mi)))
+    return md.value, (-1 if mi.value == 2**64 - 1 else mi.value)
 
 
 def raw_accumulators(distance_engine, masks_engine, db: Database, row_begin: int, row_end: int) -> np.ndarray:

@@ -92,6 +92,8 @@ struct iris_db {
     void* d_stage = nullptr;         // loader staging (reference-layout rows)
     uint16_t* d_res[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][dist|den]
     uint64_t res_rows = 0;
+    uint8_t* d_red = nullptr;        // match_min: results + reduction scratch
+    uint64_t red_rows = 0;
     int* d_error = nullptr;
 };
 
@@ -210,6 +212,7 @@ extern "C" int iris_db_destroy(iris_db* db) {
     cudaFree(db->d_shares);
     cudaFree(db->d_masks);
     cudaFree(db->d_stage);
+    cudaFree(db->d_red);
     cudaFree(db->d_error);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 2; ++k) cudaFree(db->d_res[b][k]);
@@ -756,6 +759,185 @@ extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engine
         cudaFree(d_out);
     }
     return rc;
+}
+
+// ------------------------------------------------------------------------------------ flat-file loader (f-2)
+// The reference's on-disk formats (written by `prepare`, src/main.rs:337-371; mapped by the participant and the
+// coordinator, src/main.rs:386-400, 458-461): raw EncodedBits rows (25 600 B) / raw Bits rows (1 600 B), the row
+// index being the join key.  file -> pinned staging (pread) -> H2D -> retile, double buffered.
+static int load_file(iris_db* db, const char* path, uint64_t first_row, uint64_t n_rows, bool shares) {
+    if (!db || !path) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (shares && !(db->flags & IRIS_DB_SHARES)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_SHARES");
+    if (!shares && !(db->flags & IRIS_DB_MASKS)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_MASKS");
+    const size_t row_bytes = shares ? IRIS_BITS * sizeof(uint16_t) : IRIS_MASK_BYTES;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(IRIS_ERR_INVALID, "cannot open %s", path);
+    int rc = IRIS_OK;
+    void* pinned[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    DeviceGuard g(db->device);
+    auto body = [&]() -> int {
+        if (fseeko(f, 0, SEEK_END) != 0) return fail(IRIS_ERR_INVALID, "cannot seek %s", path);
+        const uint64_t size = (uint64_t)ftello(f);
+        // reference: try_cast_slice fails -> "Share file invalid" / "Masks file invalid" (src/main.rs:391-392, 460-461)
+        if (size % row_bytes) return fail(IRIS_ERR_INVALID, "%s: size %llu is not a multiple of %zu", path, (unsigned long long)size, row_bytes);
+        const uint64_t file_rows = size / row_bytes;
+        if (first_row > file_rows) return fail(IRIS_ERR_INVALID, "%s: first_row beyond the %llu rows of the file", path, (unsigned long long)file_rows);
+        const uint64_t n = n_rows ? n_rows : file_rows - first_row;
+        if (first_row + n > file_rows) return fail(IRIS_ERR_INVALID, "%s: row range beyond the %llu rows of the file", path, (unsigned long long)file_rows);
+        uint64_t& have = shares ? db->n_shares : db->n_masks;
+        if (have + n > db->capacity) return fail(IRIS_ERR_INVALID, "load of %llu rows exceeds capacity %llu", (unsigned long long)n, (unsigned long long)db->capacity);
+        const uint64_t chunk_rows = shares ? kStageRows / 2 : kStageRows * 8;      // 26 MB per buffer
+        const size_t chunk_bytes = chunk_rows * row_bytes;
+        int r = ensure_stage(db);                                                 // device staging holds two chunks
+        if (r) return r;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaHostAlloc(&pinned[i], chunk_bytes, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        if (fseeko(f, (off_t)(first_row * row_bytes), SEEK_SET) != 0) return fail(IRIS_ERR_INVALID, "cannot seek %s", path);
+        uint64_t off = 0;
+        for (uint64_t i = 0; off < n; ++i) {
+            const int b = (int)(i & 1);
+            const uint64_t m = std::min(chunk_rows, n - off);
+            if (i >= 2) CK(cudaEventSynchronize(done[b]));                        // buffer b free again
+            if (fread(pinned[b], row_bytes, m, f) != m) return fail(IRIS_ERR_INVALID, "%s: short read", path);
+            uint8_t* d_stage = static_cast<uint8_t*>(db->d_stage) + (size_t)b * chunk_bytes;
+            CK(cudaMemcpyAsync(d_stage, pinned[b], m * row_bytes, cudaMemcpyHostToDevice, db->stream));
+            if (shares) CK(launch_retile_shares(reinterpret_cast<const uint16_t*>(d_stage), m, db->d_shares, have + off, db->stream));
+            else CK(launch_retile_masks(d_stage, m, db->d_masks, have + off, db->stream));
+            CK(cudaEventRecord(done[b], db->stream));
+            off += m;
+        }
+        CK(cudaStreamSynchronize(db->stream));
+        have += n;
+        return IRIS_OK;
+    };
+    rc = body();
+    cudaStreamSynchronize(db->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (pinned[i]) cudaFreeHost(pinned[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+    }
+    fclose(f);
+    return rc;
+}
+
+extern "C" int iris_db_load_shares_file(iris_db* db, const char* path, uint64_t first_row, uint64_t n_rows) {
+    return load_file(db, path, first_row, n_rows, true);
+}
+extern "C" int iris_db_load_masks_file(iris_db* db, const char* path, uint64_t first_row, uint64_t n_rows) {
+    return load_file(db, path, first_row, n_rows, false);
+}
+
+// ------------------------------------------------------------------------------------ coordinator reduction (f-1)
+extern "C" int iris_combine_min(int device, const uint16_t* const* distance_shares, uint32_t parties,
+                                const uint16_t* denominators, uint64_t n, uint64_t index_base, double* distances_out,
+                                double* min_distance, uint64_t* min_index) {
+    if (!distance_shares || !denominators || !min_distance || !min_index) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (parties == 0 || parties > (uint32_t)kMaxParties) return fail(IRIS_ERR_INVALID, "parties must be in [1,%d]", kMaxParties);
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    std::vector<void*> owned;
+    auto cleanup = [&]() {
+        for (void* q : owned) cudaFree(q);
+    };
+    auto to_device = [&](const void* src, size_t bytes, const void** out) -> int {
+        if (is_device_pointer(src) || bytes == 0) {
+            *out = src;
+            return IRIS_OK;
+        }
+        void* d = nullptr;
+        CK(cudaMalloc(&d, bytes));
+        owned.push_back(d);
+        CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+        *out = d;
+        return IRIS_OK;
+    };
+    auto body = [&]() -> int {
+        CombineParams p{};
+        p.parties = parties;
+        p.n = n;
+        p.index_base = index_base;
+        const size_t bytes = n * kOutRowBytes;
+        for (uint32_t i = 0; i < parties; ++i) {
+            if (!distance_shares[i]) return fail(IRIS_ERR_INVALID, "share %u is NULL", i);
+            int r = to_device(distance_shares[i], bytes, reinterpret_cast<const void**>(&p.shares[i]));
+            if (r) return r;
+        }
+        int r = to_device(denominators, bytes, reinterpret_cast<const void**>(&p.denominators));
+        if (r) return r;
+        const bool dist_dev = distances_out && is_device_pointer(distances_out);
+        double* d_dist = nullptr;
+        if (distances_out) {
+            if (dist_dev) d_dist = distances_out;
+            else {
+                CK(cudaMalloc(&d_dist, n * sizeof(double) + 8));
+                owned.push_back(d_dist);
+            }
+        }
+        p.distances_out = d_dist;
+        void* scratch = nullptr;
+        CK(cudaMalloc(&scratch, combine_scratch_bytes(n) + 16));
+        owned.push_back(scratch);
+        void* result = static_cast<uint8_t*>(scratch) + (combine_scratch_bytes(n) / 16) * 16;
+        CK(launch_combine_min(p, scratch, result, cudaStreamPerThread));
+        struct { double v; unsigned long long i; } h;
+        CK(cudaMemcpyAsync(&h, result, sizeof h, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+        if (distances_out && !dist_dev)
+            CK(cudaMemcpyAsync(distances_out, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        *min_distance = h.v;
+        *min_index = h.i;
+        return IRIS_OK;
+    };
+    rc = body();
+    cudaStreamSynchronize(cudaStreamPerThread);
+    cleanup();
+    return rc;
+}
+
+// Fused scan + reduction on a resident shard holding the full (n = 1 share) encodings: both engines over
+// rows [row_begin,row_end), then decode + min/argmin on the device; only 16 bytes come back.
+extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
+                                       uint64_t row_end, uint64_t index_base, double* min_distance, uint64_t* min_index) {
+    if (!de || !me || !db || !min_distance || !min_index) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (row_end < row_begin) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    DeviceGuard g(db->device);
+    const uint64_t n = row_end - row_begin;
+    if (db->red_rows < n) {
+        cudaFree(db->d_red);
+        db->d_red = nullptr;
+        db->red_rows = 0;
+        const size_t row_bytes = (n * kOutRowBytes + 63) / 64 * 64;
+        CK(cudaMalloc(&db->d_red, 2 * row_bytes + combine_scratch_bytes(n) + 64));
+        db->red_rows = n;
+    }
+    const size_t row_bytes = (n * kOutRowBytes + 63) / 64 * 64;
+    uint16_t* d_dist = reinterpret_cast<uint16_t*>(db->d_red);
+    uint16_t* d_den = reinterpret_cast<uint16_t*>(db->d_red + row_bytes);
+    uint8_t* scratch = db->d_red + 2 * row_bytes;
+    void* result = scratch + (combine_scratch_bytes(n) / 16) * 16 + 16;
+    if (n) {
+        int rc = scan_core(db, de->d_qd, me->d_qm, row_begin, row_end, d_dist, d_den, nullptr);
+        if (rc) return rc;
+    }
+    CombineParams p{};
+    p.shares[0] = d_dist;
+    p.parties = 1;
+    p.denominators = d_den;
+    p.n = n;
+    p.index_base = index_base + row_begin;
+    CK(launch_combine_min(p, scratch, result, db->stream));
+    struct { double v; unsigned long long i; } h;
+    CK(cudaMemcpyAsync(&h, result, sizeof h, cudaMemcpyDeviceToHost, db->stream));
+    CK(cudaStreamSynchronize(db->stream));
+    int rc = check_error_flag(db);
+    if (rc) return rc;
+    *min_distance = h.v;
+    *min_index = h.i;
+    return IRIS_OK;
 }
 
 // ------------------------------------------------------------------------------------ per-pair arch entry points

@@ -78,6 +78,19 @@ struct BatchMaskParams {
 };
 cudaError_t launch_batch_denominators(const BatchMaskParams& p, int num_sms, cudaStream_t stream);
 
+// Coordinator reduction (iris_reduce.cu): wrapping sum of party shares, decode_distance, min / argmin.
+constexpr int kMaxParties = 8;
+struct CombineParams {
+    const uint16_t* shares[kMaxParties];   // each [n][31] u16 (device)
+    uint32_t parties;
+    const uint16_t* denominators;          // [n][31] u16 (device)
+    uint64_t n;
+    uint64_t index_base;                   // added to the row number in the reported argmin
+    double* distances_out;                 // optional [n] f64 (device)
+};
+size_t combine_scratch_bytes(uint64_t n);
+cudaError_t launch_combine_min(const CombineParams& p, void* scratch, void* result, cudaStream_t stream);
+
 // Number of kernels launched by this library since load (bench.py's gpu_launches).
 uint64_t launch_count();
 

@@ -1,0 +1,111 @@
+// Coordinator-side reduction on the device:
+//   numerator[r] = wrapping sum over parties of the distance shares          src/main.rs:603-608
+//   decode_distance: min_r ((den - num) as u16 / 2) as f64 / den as f64       src/lib.rs:97-107
+//                    (f64::min ignores NaN, so den = 0 with num = 0 is skipped; x/0 = +inf)
+//   running min / argmin over rows with `distance < min_distance`             src/main.rs:611-621
+//                    (strict <: the FIRST row attaining the minimum wins)
+// IEEE-754 double division on the device is correctly rounded, so the result is bit-identical
+// to the CPU's.  Collapses 124 bytes per row to 16 bytes per query, which is what makes the
+// multi-GPU exchange "small vectors" (DESIGN.md section 7).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "iris_kernels.cuh"
+
+namespace iris {
+
+void count_launch_external();
+
+constexpr int kReduceThreads = 256;
+
+__device__ __forceinline__ void min_pair(double& v, unsigned long long& i, double ov, unsigned long long oi) {
+    if (ov < v || (ov == v && oi < i)) {
+        v = ov;
+        i = oi;
+    }
+}
+
+__global__ void __launch_bounds__(kReduceThreads) combine_decode_kernel(const CombineParams p, double* __restrict__ block_min,
+                                                                        unsigned long long* __restrict__ block_idx) {
+    __shared__ double s_v[kReduceThreads / 32];
+    __shared__ unsigned long long s_i[kReduceThreads / 32];
+    const uint64_t row = (uint64_t)blockIdx.x * kReduceThreads + threadIdx.x;
+    double best = CUDART_INF;
+    unsigned long long idx = ~0ull;
+    if (row < p.n) {
+        const uint16_t* den = p.denominators + row * IRIS_ROTATIONS;
+#pragma unroll
+        for (int j = 0; j < IRIS_ROTATIONS; ++j) {
+            uint32_t s = 0;
+            for (uint32_t q = 0; q < p.parties; ++q) s += p.shares[q][row * IRIS_ROTATIONS + j];
+            const uint16_t d = den[j];
+            const uint16_t num = (uint16_t)((uint16_t)(d - (uint16_t)s) >> 1);
+            best = fmin(best, (double)num / (double)d);      // fmin drops a NaN operand like f64::min
+        }
+        idx = p.index_base + row;
+        if (p.distances_out) p.distances_out[row] = best;
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const unsigned long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        min_pair(best, idx, ov, oi);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_v[threadIdx.x >> 5] = best;
+        s_i[threadIdx.x >> 5] = idx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kReduceThreads / 32; ++w) min_pair(best, idx, s_v[w], s_i[w]);
+        block_min[blockIdx.x] = best;
+        block_idx[blockIdx.x] = idx;
+    }
+}
+
+__global__ void __launch_bounds__(kReduceThreads) final_min_kernel(const double* __restrict__ block_min,
+                                                                   const unsigned long long* __restrict__ block_idx, uint32_t n,
+                                                                   double* __restrict__ out_min,
+                                                                   unsigned long long* __restrict__ out_idx) {
+    __shared__ double s_v[kReduceThreads / 32];
+    __shared__ unsigned long long s_i[kReduceThreads / 32];
+    double best = CUDART_INF;
+    unsigned long long idx = ~0ull;
+    for (uint32_t k = threadIdx.x; k < n; k += kReduceThreads) min_pair(best, idx, block_min[k], block_idx[k]);
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const unsigned long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        min_pair(best, idx, ov, oi);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_v[threadIdx.x >> 5] = best;
+        s_i[threadIdx.x >> 5] = idx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kReduceThreads / 32; ++w) min_pair(best, idx, s_v[w], s_i[w]);
+        *out_min = best;
+        *out_idx = best < CUDART_INF ? idx : ~0ull;   // nothing was `< INFINITY`: min_index stays usize::MAX (main.rs:582)
+    }
+}
+
+size_t combine_scratch_bytes(uint64_t n) {
+    const uint64_t blocks = (n + kReduceThreads - 1) / kReduceThreads;
+    return blocks * (sizeof(double) + sizeof(unsigned long long)) + 64;
+}
+
+// scratch: combine_scratch_bytes(n) device bytes; result: device {double min; u64 index} (16 bytes)
+cudaError_t launch_combine_min(const CombineParams& p, void* scratch, void* result, cudaStream_t stream) {
+    const uint32_t blocks = (uint32_t)((p.n + kReduceThreads - 1) / kReduceThreads);
+    double* bmin = static_cast<double*>(scratch);
+    unsigned long long* bidx = reinterpret_cast<unsigned long long*>(bmin + blocks);
+    if (blocks) {
+        combine_decode_kernel<<<blocks, kReduceThreads, 0, stream>>>(p, bmin, bidx);
+        count_launch_external();
+    }
+    final_min_kernel<<<1, kReduceThreads, 0, stream>>>(bmin, bidx, blocks, static_cast<double*>(result),
+                                                      reinterpret_cast<unsigned long long*>(static_cast<double*>(result) + 1));
+    count_launch_external();
+    return cudaGetLastError();
+}
+
+}  // namespace iris

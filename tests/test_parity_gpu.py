@@ -430,3 +430,91 @@ def test_denominators_batch_matches_per_engine_and_oracle(iris, small, nq):
     single = np.zeros((1000, 31), np.uint16)
     engines[-1].batch_process(single, db)
     assert np.array_equal(single, exp[-1])
+
+
+# ----------------------------------------------------------------------------------- coordinator reduction (f-1)
+def test_combine_min_matches_reference_coordinator(iris, small):
+    """iris_combine_min == wrapping sum of party shares + decode_distance + running min (src/main.rs:597-621,
+    src/lib.rs:97-107), bit-exact in f64, first minimum wins."""
+    r = np.random.default_rng(60)
+    n = 600
+    qp, qm = O.gen_mask_rows(61, 0, 1)[0], O.gen_mask_rows(61, 1, 1)[0]
+    ep, em = O.gen_mask_rows(62, 0, n), O.gen_mask_rows(63, 0, n)
+    ep[417], em[417] = qp, qm                      # exact match
+    ep[99], em[99] = qp, qm                        # equal distance earlier: must win
+    em[5] = 0                                      # fully masked row: den = 0 -> NaN / inf handling
+    enc = np.stack([O.encode(ep[i], em[i]) for i in range(n)])
+    s0 = r.integers(0, 2**16, size=enc.shape, dtype=np.uint16)
+    s1 = r.integers(0, 2**16, size=enc.shape, dtype=np.uint16)
+    s2 = (enc - s0 - s1).astype(np.uint16)
+    q = O.encode(qp, qm)
+    shares = [O.distance_batch(q, s, threads=8) for s in (s0, s1, s2)]
+    den = O.masks_batch(qm, em, threads=8)
+    exp_min, exp_idx = O.combine_min(np.stack(shares), den)
+    md, mi, dist = iris.combine_min(shares, den, want_distances=True)
+    assert (md, mi) == (exp_min, exp_idx) == (0.0, 99)
+    exp_dist = np.array([O.decode_distance((shares[0][i] + shares[1][i] + shares[2][i]).astype(np.uint16), den[i]) for i in range(n)])
+    assert np.array_equal(dist, exp_dist)          # bit-exact f64, including the +inf of the masked-out row
+    assert dist[5] == np.inf
+    assert iris.combine_min(shares, den, index_base=1000) == (0.0, 1099)
+    # nothing below +inf: the reference leaves min_index = usize::MAX
+    z = np.zeros((4, 31), np.uint16)
+    assert iris.combine_min([z], z) == (np.inf, -1)
+
+
+def test_match_min_fused_scan_and_reduction(iris):
+    n = 3000
+    qp, qm = O.gen_mask_rows(71, 0, 1)[0], O.gen_mask_rows(71, 1, 1)[0]
+    ep, em = O.gen_mask_rows(72, 0, n), O.gen_mask_rows(73, 0, n)
+    noisy = qp.copy()
+    noisy[:3] ^= np.uint64(0xFFFF)                 # near match at row 2222
+    ep[2222], em[2222] = noisy, qm
+    enc = np.stack([O.encode(ep[i], em[i]) for i in range(n)])
+    q = O.encode(qp, qm)
+    with iris.Database(n) as db:
+        db.append_shares(enc)
+        db.append_masks(em)
+        de, me = iris.DistanceEngine(q), iris.MasksEngine(qm)
+        exp = O.combine_min(O.distance_batch(q, enc, threads=8)[None], O.masks_batch(qm, em, threads=8))
+        assert iris.match_min(de, me, db, 0, n) == exp
+        assert exp[1] == 2222
+        exp_sub = O.combine_min(O.distance_batch(q, enc[100:2000], threads=8)[None], O.masks_batch(qm, em[100:2000], threads=8))
+        assert iris.match_min(de, me, db, 100, 2000, index_base=50_000) == (exp_sub[0], 50_000 + 100 + exp_sub[1])
+        plain = min(O.template_distance(qp, qm, ep[i], em[i]) for i in (2222, 7, 1234))
+        assert abs(exp[0] - plain) <= np.spacing(plain)
+
+
+# ----------------------------------------------------------------------------------- flat-file loader (f-2)
+def test_flat_file_loader_reads_reference_formats(iris, tmp_path):
+    """mpc.share-i = raw EncodedBits rows, mpc.masks = raw Bits rows (src/main.rs:337-371, 386-400, 458-461)."""
+    n = 2500                                        # > one 1024-row staging chunk: exercises the double buffer
+    shares = O.gen_share_rows(SEED, 0, n, threads=8)
+    masks = O.gen_mask_rows(SEED, 0, n, threads=8)
+    sp, mp_ = tmp_path / "mpc.share-0", tmp_path / "mpc.masks"
+    shares.tofile(sp)
+    masks.tofile(mp_)
+    with iris.Database(n + 10) as db:
+        db.load_shares_file(str(sp))
+        db.load_masks_file(str(mp_), 0, 1000)
+        db.load_masks_file(str(mp_), 1000)           # the rest
+        assert (db.len_shares, db.len_masks) == (n, n)
+        assert np.array_equal(db.read_shares(0, n), shares)
+        assert np.array_equal(db.read_masks(0, n), masks)
+        q, _, qm = ternary_query(77)
+        d, den = np.zeros((n, 31), np.uint16), np.zeros((n, 31), np.uint16)
+        iris.match(iris.DistanceEngine(q), iris.MasksEngine(qm), db, 0, n, d, den)
+        assert np.array_equal(d, O.distance_batch(q, shares, threads=8))
+        assert np.array_equal(den, O.masks_batch(qm, masks, threads=8))
+    with iris.Database(100) as db:
+        db.load_shares_file(str(sp), 2400, 100)      # a row window of the file
+        assert np.array_equal(db.read_shares(0, 100), shares[2400:])
+        with pytest.raises(iris.IrisError):
+            db.load_shares_file(str(sp), 0, 10)      # exceeds capacity
+        with pytest.raises(iris.IrisError):
+            db.load_shares_file(str(tmp_path / "missing"))
+    bad = tmp_path / "truncated"
+    bad.write_bytes(shares.tobytes()[:-7])           # not a whole number of rows: "Share file invalid"
+    with iris.Database(n) as db:
+        with pytest.raises(iris.IrisError) as ei:
+            db.load_shares_file(str(bad))
+        assert ei.value.code == -1
