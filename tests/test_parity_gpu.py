@@ -509,7 +509,7 @@ def test_flat_file_loader_reads_reference_formats(iris, tmp_path):
         db.load_shares_file(str(sp), 2400, 100)      # a row window of the file
         assert np.array_equal(db.read_shares(0, 100), shares[2400:])
         with pytest.raises(iris.IrisError):
-            db.load_shares_file(str(sp), 0, 10)      # exceeds capacity
+            db.load_shares_file(str(sp), 0, 200)     # exceeds capacity (100 rounds up to one 256-row pair tile)
         with pytest.raises(iris.IrisError):
             db.load_shares_file(str(tmp_path / "missing"))
     bad = tmp_path / "truncated"
