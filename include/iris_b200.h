@@ -97,6 +97,13 @@ int iris_db_synchronize(iris_db *db);
 /* ---- DistanceEngine (src/lib.rs:28-52) ---- */
 /* new: prepares the 31 rotations (-15..=15) of `query` as the tensor-core operand image. */
 int iris_distance_engine_new(int device, const uint16_t query[IRIS_BITS], iris_distance_engine **out);
+/* DistanceEngine::new(&encode(&template)) as the participant does per request (src/main.rs:427): encode
+ * (src/lib.rs:16-26) and the rotation preparation both run on the device from the wire Template. */
+int iris_distance_engine_new_from_template(int device, const uint64_t pattern[IRIS_LIMBS],
+                                           const uint64_t mask[IRIS_LIMBS], iris_distance_engine **out);
+/* encode(&Template) -> EncodedBits (src/lib.rs:16-26), computed on the device; out host or device. */
+int iris_encode(int device, const uint64_t pattern[IRIS_LIMBS], const uint64_t mask[IRIS_LIMBS],
+                uint16_t out[IRIS_BITS]);
 int iris_distance_engine_free(iris_distance_engine *e);
 /* batch_process(&self, out, db) with the reference's exact shape: `db` is a HOST slice of
  * db_len EncodedBits, `out` a HOST slice of out_len [u16;31]; out_len != db_len is an error.

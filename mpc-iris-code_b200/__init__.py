@@ -25,6 +25,7 @@ from .api import (  # noqa: F401
     distances,
     distances_batch,
     dot_bool,
+    encode,
     dot_u16,
     launch_count,
     lib,

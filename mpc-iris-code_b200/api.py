@@ -68,6 +68,8 @@ def lib():
         "iris_db_synchronize": [vp],
         "iris_distance_engine_new": [i32, vp, pp],
         "iris_distance_engine_free": [vp],
+        "iris_distance_engine_new_from_template": [i32, vp, vp, pp],
+        "iris_encode": [i32, vp, vp, vp],
         "iris_distance_engine_batch_process": [vp, vp, u64, vp, u64],
         "iris_distance_engine_batch_process_resident": [vp, vp, u64, vp, u64, u64],
         "iris_masks_engine_new": [i32, vp, pp],
@@ -267,13 +269,31 @@ def _out_len(out) -> int:
 
 
 # ------------------------------------------------------------------ engines
+def encode(pattern, mask, device: int = 0) -> np.ndarray:
+    """encode(&Template) -> EncodedBits (src/lib.rs:16-26), on the device."""
+    out = np.empty(BITS, np.uint16)
+    _check(lib().iris_encode(device, _ptr(pattern, np.uint64, LIMBS, "pattern"), _ptr(mask, np.uint64, LIMBS, "mask"), out.ctypes.data))
+    return out
+
+
 class DistanceEngine:
     """DistanceEngine (src/lib.rs:28-52): new(query) prepares rotations -15..=15; batch_process fills out[i][j]."""
 
-    def __init__(self, query, device: int = 0):
+    def __init__(self, query, device: int = 0, _handle=None):
         self._h = ctypes.c_void_p()
         self.device = device
+        if _handle is not None:
+            self._h = _handle
+            return
         _check(lib().iris_distance_engine_new(device, _ptr(query, np.uint16, BITS, "query"), ctypes.byref(self._h)))
+
+    @classmethod
+    def from_template(cls, pattern, mask, device: int = 0) -> "DistanceEngine":
+        """DistanceEngine::new(&encode(&template)) (src/main.rs:427) with encode done on the device."""
+        h = ctypes.c_void_p()
+        _check(lib().iris_distance_engine_new_from_template(
+            device, _ptr(pattern, np.uint64, LIMBS, "pattern"), _ptr(mask, np.uint64, LIMBS, "mask"), ctypes.byref(h)))
+        return cls(None, device, _handle=h)
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:

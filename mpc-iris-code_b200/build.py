@@ -61,7 +61,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
     os.replace(tmp, LIB_PATH)
+    build_participant()
     return LIB_PATH
+
+
+BIN_DIR = os.path.join(HERE, "bin")
+PARTICIPANT_PATH = os.path.join(BIN_DIR, "iris_participant")
+
+
+def build_participant() -> str:
+    """The wire-protocol front-end (reference `participant`, src/main.rs:384-452) over the C ABI: plain g++."""
+    os.makedirs(BIN_DIR, exist_ok=True)
+    tmp = PARTICIPANT_PATH + f".tmp{os.getpid()}"
+    subprocess.check_call([
+        "g++", "-O2", "-std=c++17", "-o", tmp, os.path.join(CSRC, "participant_main.cpp"),
+        "-L" + LIB_DIR, "-liris_b200", "-Wl,-rpath,$ORIGIN/../lib",
+    ])
+    os.replace(tmp, PARTICIPANT_PATH)
+    return PARTICIPANT_PATH
 
 
 if __name__ == "__main__":

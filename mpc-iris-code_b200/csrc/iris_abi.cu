@@ -506,6 +506,77 @@ extern "C" int iris_distance_engine_new(int device, const uint16_t* query, iris_
     return IRIS_OK;
 }
 
+// encode(&Template) (src/lib.rs:16-26) on the device; `out` host or device.
+extern "C" int iris_encode(int device, const uint64_t* pattern, const uint64_t* mask, uint16_t* out) {
+    if (!pattern || !mask || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(&d, 2 * IRIS_MASK_BYTES + IRIS_BITS * sizeof(uint16_t)));
+    auto body = [&]() -> int {
+        uint16_t* d_out = reinterpret_cast<uint16_t*>(d + 2 * IRIS_MASK_BYTES);
+        CK(cudaMemcpyAsync(d, pattern, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+        CK(cudaMemcpyAsync(d + IRIS_MASK_BYTES, mask, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+        CK(launch_encode(d, d + IRIS_MASK_BYTES, d_out, cudaStreamPerThread));
+        CK(cudaMemcpyAsync(out, d_out, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDefault, cudaStreamPerThread));
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        return IRIS_OK;
+    };
+    rc = body();
+    cudaFree(d);
+    return rc;
+}
+
+// DistanceEngine::new(&encode(&template)) as the participant does per request (src/main.rs:427): the 3 200-byte
+// wire Template goes to the device, encode + rotation preparation run there.
+extern "C" int iris_distance_engine_new_from_template(int device, const uint64_t* pattern, const uint64_t* mask,
+                                                      iris_distance_engine** out) {
+    if (!pattern || !mask || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
+    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    uint8_t* d_t = nullptr;
+    auto body = [&]() -> int {
+        int r = pooled_alloc(g_pool.q16, device, IRIS_BITS * sizeof(uint16_t), reinterpret_cast<void**>(&e->d_query));
+        if (r) return r;
+        r = pooled_alloc(g_pool.qd, device, kQdBytes, reinterpret_cast<void**>(&e->d_qd));
+        if (r) return r;
+        r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&d_t));
+        if (r) return r;
+        uint8_t* d_m = nullptr;
+        r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&d_m));
+        if (r) return r;
+        int rr = IRIS_OK;
+        auto inner = [&]() -> int {
+            CK(cudaMemcpyAsync(d_t, pattern, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+            CK(cudaMemcpyAsync(d_m, mask, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+            CK(launch_encode(d_t, d_m, e->d_query, cudaStreamPerThread));
+            CK(launch_prep_distance_query(e->d_query, e->d_qd, cudaStreamPerThread));
+            CK(cudaStreamSynchronize(cudaStreamPerThread));
+            return IRIS_OK;
+        };
+        rr = inner();
+        g_pool.give(g_pool.q8, device, d_m);
+        e->fits_s8 = true;                           // encode() only yields 0, 1, 0xFFFF
+        return rr;
+    };
+    rc = body();
+    g_pool.give(g_pool.q8, device, d_t);
+    if (rc) {
+        std::string keep = g_last_error;
+        iris_distance_engine_free(e);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = e;
+    return IRIS_OK;
+}
+
 extern "C" int iris_distance_engine_free(iris_distance_engine* e) {
     if (!e) return IRIS_OK;
     DeviceGuard g(e->device);

@@ -364,6 +364,21 @@ __global__ void prep_mask_query_kernel(const uint8_t* __restrict__ qmask, uint8_
     *reinterpret_cast<uint4*>(qm + off) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// encode (src/lib.rs:16-26): mask - 2*(pattern & mask) in Z/2^16 -> 1 (mask & !pattern), 0 (!mask), 0xFFFF (mask & pattern)
+__global__ void encode_kernel(const uint8_t* __restrict__ pattern, const uint8_t* __restrict__ mask,
+                              uint16_t* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= IRIS_BITS) return;
+    const uint32_t m = (mask[k >> 3] >> (k & 7)) & 1u;
+    const uint32_t p = (pattern[k >> 3] >> (k & 7)) & m;
+    out[k] = (uint16_t)(m - p - p);
+}
+cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint16_t* d_out, cudaStream_t stream) {
+    encode_kernel<<<(IRIS_BITS + 255) / 256, 256, 0, stream>>>(d_pattern, d_mask, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_prep_distance_query(const uint16_t* d_query, uint8_t* d_qd, cudaStream_t stream) {
     prep_distance_query_kernel<<<(kChunks * 32 * 8 + 255) / 256, 256, 0, stream>>>(d_query, d_qd);
     count_launch();

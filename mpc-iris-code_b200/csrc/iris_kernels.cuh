@@ -26,6 +26,7 @@ struct ScanParams {
 cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
 
 // Query preparation (K3): reference DistanceEngine::new / MasksEngine::new (src/lib.rs:33-40, 60-67).
+cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint16_t* d_out, cudaStream_t stream);
 cudaError_t launch_prep_distance_query(const uint16_t* d_query, uint8_t* d_qd, cudaStream_t stream);
 cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, cudaStream_t stream);
 

@@ -1,0 +1,177 @@
+// iris_participant -- wire-compatible stand-in for the reference's `participant` subcommand
+// (src/main.rs:384-452) on top of the C ABI, with the share database resident in HBM.
+//
+// Protocol (raw native-endian Pod bytes, no framing; src/main.rs:418-443):
+//   request : one 3 200-byte Template {pattern: Bits, mask: Bits}           (src/template.rs:11-29)
+//   reply   : [u16;31] per database row (62 bytes, rotation -15..=15), produced in batches of
+//             20 000 rows (src/main.rs:428, 473) and streamed back; EOF terminates the reply.
+// One request at a time, like the reference.  An unmodified reference coordinator / benchmark
+// (src/main.rs:486-504, 645-686) can connect to this process.
+//
+//   iris_participant --input mpc.share-0 [--bind 127.0.0.1:1234] [--device 0] [--batch-size 20000]
+//                    [--max-requests N] [--synthetic ROWS --seed S]
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <csignal>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/iris_b200.h"
+
+static void die(const char* what) {
+    fprintf(stderr, "iris_participant: %s: %s\n", what, iris_last_error());
+    exit(1);
+}
+
+static bool read_exact(int fd, void* buf, size_t n) {
+    uint8_t* p = static_cast<uint8_t*>(buf);
+    while (n) {
+        ssize_t r = read(fd, p, n);
+        if (r == 0) return false;
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += r;
+        n -= (size_t)r;
+    }
+    return true;
+}
+
+static bool write_all(int fd, const void* buf, size_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(buf);
+    while (n) {
+        ssize_t r = write(fd, p, n);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += r;
+        n -= (size_t)r;
+    }
+    return true;
+}
+
+int main(int argc, char** argv) {
+    std::string input, bind_addr = "127.0.0.1:1234";   // reference default, src/main.rs:124
+    int device = 0;
+    uint64_t batch = 20000, synthetic = 0, seed = 0x1715C0DE;
+    long max_requests = -1;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* {
+            if (i + 1 >= argc) {
+                fprintf(stderr, "missing value for %s\n", a.c_str());
+                exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--input") input = next();
+        else if (a == "--bind") bind_addr = next();
+        else if (a == "--device") device = atoi(next());
+        else if (a == "--batch-size") batch = strtoull(next(), nullptr, 10);
+        else if (a == "--max-requests") max_requests = atol(next());
+        else if (a == "--synthetic") synthetic = strtoull(next(), nullptr, 10);
+        else if (a == "--seed") seed = strtoull(next(), nullptr, 0);
+        else {
+            fprintf(stderr, "unknown argument %s\n", a.c_str());
+            return 2;
+        }
+    }
+    if (input.empty() && !synthetic) {
+        fprintf(stderr, "usage: iris_participant --input <share file> | --synthetic <rows> [--bind host:port]\n");
+        return 2;
+    }
+    if (batch == 0) batch = 20000;
+    signal(SIGPIPE, SIG_IGN);
+
+    // "Opened share ... with N encrypted patterns" (src/main.rs:386-400): here the file goes to HBM once.
+    uint64_t rows = synthetic;
+    if (!synthetic) {
+        struct stat st;
+        if (stat(input.c_str(), &st) != 0) {
+            fprintf(stderr, "Failed to open share at %s\n", input.c_str());
+            return 1;
+        }
+        if (st.st_size % (IRIS_BITS * 2)) {
+            fprintf(stderr, "Share file %s invalid.\n", input.c_str());
+            return 1;
+        }
+        rows = (uint64_t)st.st_size / (IRIS_BITS * 2);
+    }
+    iris_db* db = nullptr;
+    if (iris_db_create(device, rows ? rows : 1, IRIS_DB_SHARES, &db)) die("iris_db_create");
+    if (synthetic) {
+        if (iris_db_generate(db, seed, 0, rows)) die("iris_db_generate");
+    } else if (rows) {
+        if (iris_db_load_shares_file(db, input.c_str(), 0, 0)) die("iris_db_load_shares_file");
+    }
+    fprintf(stderr, "Opened share with %llu encrypted patterns (resident in HBM on device %d)\n", (unsigned long long)rows, device);
+
+    const size_t colon = bind_addr.rfind(':');
+    if (colon == std::string::npos) {
+        fprintf(stderr, "bad --bind %s\n", bind_addr.c_str());
+        return 2;
+    }
+    sockaddr_in addr{};
+    addr.sin_family = AF_INET;
+    addr.sin_port = htons((uint16_t)atoi(bind_addr.c_str() + colon + 1));
+    if (inet_pton(AF_INET, bind_addr.substr(0, colon).c_str(), &addr.sin_addr) != 1) {
+        fprintf(stderr, "bad --bind %s\n", bind_addr.c_str());
+        return 2;
+    }
+    int ls = socket(AF_INET, SOCK_STREAM, 0);
+    int one = 1;
+    setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+    if (bind(ls, reinterpret_cast<sockaddr*>(&addr), sizeof addr) != 0 || listen(ls, 16) != 0) {
+        fprintf(stderr, "Could not bind to socket %s: %s\n", bind_addr.c_str(), strerror(errno));
+        return 1;
+    }
+    socklen_t alen = sizeof addr;
+    getsockname(ls, reinterpret_cast<sockaddr*>(&addr), &alen);
+    fprintf(stderr, "Listening on %s:%d\n", bind_addr.substr(0, colon).c_str(), (int)ntohs(addr.sin_port));
+    fflush(stderr);
+
+    std::vector<uint16_t> out(batch * IRIS_ROTATIONS);
+    uint64_t tmpl[2 * IRIS_LIMBS];
+    for (long served = 0; max_requests < 0 || served < max_requests; ++served) {
+        int fd = accept(ls, nullptr, nullptr);
+        if (fd < 0) {
+            if (errno == EINTR) {
+                --served;
+                continue;
+            }
+            break;
+        }
+        setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+        if (!read_exact(fd, tmpl, sizeof tmpl)) {           // stream.read_exact(bytes_of_mut(&mut template))
+            close(fd);
+            continue;
+        }
+        fprintf(stderr, "Request received.\n");
+        iris_distance_engine* engine = nullptr;
+        if (iris_distance_engine_new_from_template(device, tmpl, tmpl + IRIS_LIMBS, &engine)) die("engine");
+        bool ok = true;
+        for (uint64_t b = 0; ok && b < rows; b += batch) {   // for chunk in patterns.chunks(20_000)
+            const uint64_t e = b + batch < rows ? b + batch : rows;
+            if (iris_distance_engine_batch_process_resident(engine, out.data(), e - b, db, b, e)) die("batch_process");
+            ok = write_all(fd, out.data(), (e - b) * IRIS_ROTATIONS * sizeof(uint16_t));
+        }
+        iris_distance_engine_free(engine);
+        close(fd);                                           // EOF = end of results
+        fprintf(stderr, ok ? "Reply sent.\n" : "Peer went away.\n");
+    }
+    close(ls);
+    iris_db_destroy(db);
+    return 0;
+}

@@ -518,3 +518,64 @@ def test_flat_file_loader_reads_reference_formats(iris, tmp_path):
         with pytest.raises(iris.IrisError) as ei:
             db.load_shares_file(str(bad))
         assert ei.value.code == -1
+
+
+# ----------------------------------------------------------------------------------- device-side encode (f-5) + wire shim (f-3)
+def test_encode_on_device_and_engine_from_template(iris, small):
+    # src/lib.rs:16-26 + test_preprocess (src/lib.rs:117-132)
+    db, shares, _ = small
+    for seed in range(80, 84):
+        p, m = O.gen_mask_rows(seed, 0, 1)[0], O.gen_mask_rows(seed, 1, 1)[0]
+        enc = iris.encode(p, m)
+        assert np.array_equal(enc, O.encode(p, m))
+        assert set(np.unique(enc)) <= {0, 1, 0xFFFF}
+    out = np.zeros((1000, 31), np.uint16)
+    iris.DistanceEngine.from_template(p, m).batch_process(out, db)
+    assert np.array_equal(out, O.distance_batch(O.encode(p, m), shares, threads=8))
+
+
+def test_participant_wire_protocol(iris, tmp_path):
+    """The C++ front-end speaks the reference participant protocol (src/main.rs:411-446): 3 200-byte Template in,
+    62 bytes per row out in batches, EOF at the end.  Played here by a Python 'coordinator'."""
+    import socket
+    import subprocess
+    import time
+
+    from mpc_iris_code_b200 import build
+
+    n = 2300
+    shares = O.gen_share_rows(SEED, 0, n, threads=8)
+    path = tmp_path / "mpc.share-0"
+    shares.tofile(path)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    exe = build.PARTICIPANT_PATH
+    if not os.path.exists(exe):
+        build.build_participant()
+    proc = subprocess.Popen([exe, "--input", str(path), "--bind", f"127.0.0.1:{port}", "--batch-size", "1000", "--max-requests", "2"],
+                            stderr=subprocess.PIPE, text=True)
+    try:
+        deadline = time.time() + 120
+        while True:                                   # wait for "Listening on"
+            line = proc.stderr.readline()
+            if "Listening on" in line:
+                break
+            assert proc.poll() is None and time.time() < deadline, line
+        for seed in (90, 91):
+            p, m = O.gen_mask_rows(seed, 0, 1)[0], O.gen_mask_rows(seed, 1, 1)[0]
+            with socket.create_connection(("127.0.0.1", port), timeout=60) as c:
+                c.sendall(p.tobytes() + m.tobytes())  # Template {pattern, mask} (src/template.rs:26-29)
+                chunks = []
+                while True:
+                    b = c.recv(1 << 20)
+                    if not b:
+                        break
+                    chunks.append(b)
+            got = np.frombuffer(b"".join(chunks), np.uint16).reshape(-1, 31)
+            assert got.shape == (n, 31)
+            assert np.array_equal(got, O.distance_batch(O.encode(p, m), shares, threads=8))
+        assert proc.wait(timeout=60) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
