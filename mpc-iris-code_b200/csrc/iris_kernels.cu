@@ -14,6 +14,7 @@
 //   popcount(qmask & dmask) = (1/128) * sum_k A[k] B[k] with A[k] = dbit << t, B[k] = qbit << (7-t),
 //   t = bit position inside the source byte; the sum <= 12800*128 < 2^31.
 #include <atomic>
+#include <cstdlib>
 
 #include "iris_kernels.cuh"
 #include "iris_ptx.cuh"
@@ -313,7 +314,16 @@ cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
     const bool s = p.shares != nullptr, m = p.masks != nullptr;
     if (s && m) return launch_scan_t<true, true>(p, num_sms, stream);
     if (s) return launch_scan_t<true, false>(p, num_sms, stream);
-    if (m) return launch_scan_t<false, true>(p, num_sms, stream);
+    if (m) {
+        // denominators only: the TMEM-operand kernel (iris_maskscan.cu); IRIS_MASKSCAN=smem selects the
+        // shared-memory-operand variant of this file (kept for A/B measurements and the raw debug dump)
+        static const bool use_smem = [] {
+            const char* e = getenv("IRIS_MASKSCAN");
+            return e && e[0] == 's';
+        }();
+        if (!use_smem && !p.raw_out) return launch_mask_scan(p, num_sms, stream);
+        return launch_scan_t<false, true>(p, num_sms, stream);
+    }
     return cudaErrorInvalidValue;
 }
 

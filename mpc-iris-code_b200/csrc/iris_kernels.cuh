@@ -24,6 +24,8 @@ struct ScanParams {
 
 // Launches the persistent tcgen05 scan.  Mode is derived from which of shares/masks is non-null.
 cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
+// Denominators-only scan with the expanded operand in tensor memory (iris_maskscan.cu).
+cudaError_t launch_mask_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
 
 // Query preparation (K3): reference DistanceEngine::new / MasksEngine::new (src/lib.rs:33-40, 60-67).
 cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint16_t* d_out, cudaStream_t stream);
