@@ -83,9 +83,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(out_stage_ptr + 2 * kBatchOutStageBytes + 8 * (3 * kStages + 2));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = ptx::warp_idx_sync();                   // warp-uniform role index
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();            // 0 = leader (issues the UMMAs)
+    const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);   // 0 = leader (issues the UMMAs)
     const uint32_t cluster_id = blockIdx.x >> 1;
     const uint32_t num_clusters = gridDim.x >> 1;
 
@@ -111,24 +111,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
 
     if (warp == 4) {
         // ------------------------------------------------------------------ producer (each CTA loads its own half)
-        if (lane == 0) {
-            const uint64_t pol_keep = ptx::policy_evict_last();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
-                const uint32_t pair = p.pair_begin + t / num_groups;
-                const uint32_t group = t % num_groups;
-                const uint8_t* sh = p.shares + (size_t)(2 * pair + rank) * kShareTileBytes;
-                const uint8_t* q[4];
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+            const uint32_t pair = p.pair_begin + t / num_groups;
+            const uint32_t group = t % num_groups;
+            const uint8_t* sh = p.shares + (size_t)(2 * pair + rank) * kShareTileBytes;
+            const uint8_t* q[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t qi = group * kBatchQTile + 4 * rank + i;
-                    q[i] = p.qd[qi < p.num_queries ? qi : p.num_queries - 1];
-                }
-                for (int c = 0; c < kChunks; ++c) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWbProducer);
-                    const uint32_t sbase = base + stage * Cfg::kStageBytes;
-                    const uint32_t fb = full_bar(stage);
+            for (int i = 0; i < 4; ++i) {
+                uint32_t qi = group * kBatchQTile + 4 * rank + i;
+                q[i] = p.qd[qi < p.num_queries ? qi : p.num_queries - 1];
+            }
+            for (int c = 0; c < kChunks; ++c) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWbProducer);
+                const uint32_t sbase = base + stage * Cfg::kStageBytes;
+                const uint32_t fb = full_bar(stage);
+                if (ptx::elect_one_sync()) {
                     ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
                     ptx::bulk_g2s(sbase + Cfg::kOffAlo, sh + (size_t)c * kShareChunkBytes, kShareChunkBytes, fb);
 #pragma unroll
@@ -139,30 +139,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
                             ptx::bulk_g2s_hint(sbase + Cfg::kOffBhi + i * kQTileBytes,
                                                q[i] + (size_t)c * kQdChunkBytes + kQTileBytes, kQTileBytes, fb, pol_keep);
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------------ stage relay (both CTAs) + UMMA issue (leader)
-        if (lane == 0) {
-            constexpr uint32_t kIdescU = ptx::umma_idesc_i8_m256(256, false, false);
-            constexpr uint32_t kIdescS = ptx::umma_idesc_i8_m256(256, false, true);
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t it = 0;
-            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        constexpr uint32_t kIdescU = ptx::umma_idesc_i8_m256(256, false, false);
+        constexpr uint32_t kIdescS = ptx::umma_idesc_i8_m256(256, false, true);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t it = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            if (rank == 0) {
+                ptx::mbar_wait(tempty_bar, (it & 1u) ^ 1u, p.error, kWbTmemEmpty);
+                ptx::tc_fence_after();
+            }
+            for (int c = 0; c < kChunks; ++c) {
+                ptx::mbar_wait(full_bar(stage), phase, p.error, kWbFull);
+                const uint32_t ready_leader = ptx::mapa(ready_bar(stage), 0);
+                if (ptx::elect_one_sync()) ptx::mbar_arrive_cluster(ready_leader);           // this half landed
+                __syncwarp();
                 if (rank == 0) {
-                    ptx::mbar_wait(tempty_bar, (it & 1u) ^ 1u, p.error, kWbTmemEmpty);
+                    ptx::mbar_wait(ready_bar(stage), phase, p.error, kWbReady);
                     ptx::tc_fence_after();
-                }
-                for (int c = 0; c < kChunks; ++c) {
-                    ptx::mbar_wait(full_bar(stage), phase, p.error, kWbFull);
-                    ptx::mbar_arrive_cluster(ptx::mapa(ready_bar(stage), 0));                // tell the leader this half landed
-                    if (rank == 0) {
-                        ptx::mbar_wait(ready_bar(stage), phase, p.error, kWbReady);
-                        ptx::tc_fence_after();
-                        const uint32_t sbase = base + stage * Cfg::kStageBytes;
+                    const uint32_t sbase = base + stage * Cfg::kStageBytes;
+                    if (ptx::elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < kChunkK / 32; ++k) {
                             const uint32_t acc = (c | k) ? 1u : 0u;
@@ -182,8 +185,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
                         ptx::umma_commit_2cta(empty_bar(stage), 3);
                         if (c == kChunks - 1) ptx::umma_commit_2cta(tfull_bar, 3);
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    __syncwarp();
                 }
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
@@ -307,9 +311,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMaskThreads, 1)
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(out_stage_ptr + 2 * kBatchOutStageBytes + 8 * (4 * kStages + 2));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = ptx::warp_idx_sync();
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
+    const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);
     const uint32_t cluster_id = blockIdx.x >> 1;
     const uint32_t num_clusters = gridDim.x >> 1;
 
@@ -336,55 +340,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMaskThreads, 1)
 
     if (warp == 4) {
         // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const uint64_t pol_keep = ptx::policy_evict_last();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
-                const uint32_t pair = p.pair_begin + t / num_groups;
-                const uint32_t group = t % num_groups;
-                const uint8_t* mk = p.masks + (size_t)(2 * pair + rank) * kMaskTileBytes;
-                // this CTA's half of both N=256 operands: queries {0..3, 8..11} (rank 0) or {4..7, 12..15} (rank 1)
-                const uint8_t* q[8];
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+            const uint32_t pair = p.pair_begin + t / num_groups;
+            const uint32_t group = t % num_groups;
+            const uint8_t* mk = p.masks + (size_t)(2 * pair + rank) * kMaskTileBytes;
+            // this CTA's half of both N=256 operands: queries {0..3, 8..11} (rank 0) or {4..7, 12..15} (rank 1)
+            const uint8_t* q[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint32_t qi = group * kMaskQTile + (i < 4 ? 4 * rank + i : 8 + 4 * rank + (i - 4));
-                    q[i] = p.qm[qi < p.num_queries ? qi : p.num_queries - 1];
-                }
-                for (int c = 0; c < kChunks; ++c) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWmProducer);
-                    const uint32_t sbase = base + stage * kMaskStageBytes;
-                    const uint32_t fb = full_bar(stage);
+            for (int i = 0; i < 8; ++i) {
+                uint32_t qi = group * kMaskQTile + (i < 4 ? 4 * rank + i : 8 + 4 * rank + (i - 4));
+                q[i] = p.qm[qi < p.num_queries ? qi : p.num_queries - 1];
+            }
+            for (int c = 0; c < kChunks; ++c) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWmProducer);
+                const uint32_t sbase = base + stage * kMaskStageBytes;
+                const uint32_t fb = full_bar(stage);
+                if (ptx::elect_one_sync()) {
                     ptx::mbar_arrive_expect_tx(fb, 8 * kQTileBytes + kMaskChunkBytes);
                     ptx::bulk_g2s(sbase + kMaskOffPk, mk + (size_t)c * kMaskChunkBytes, kMaskChunkBytes, fb);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         ptx::bulk_g2s_hint(sbase + kMaskOffB + i * kQTileBytes, q[i] + (size_t)c * kQmChunkBytes, kQTileBytes,
                                            fb, pol_keep);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------------ relay (both CTAs) + UMMA issue (leader)
-        if (lane == 0) {
-            constexpr uint32_t kIdesc = ptx::umma_idesc_i8_m256(256, false, false);
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t it = 0;
-            for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        constexpr uint32_t kIdesc = ptx::umma_idesc_i8_m256(256, false, false);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t it = 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            if (rank == 0) {
+                ptx::mbar_wait(tempty_bar, (it & 1u) ^ 1u, p.error, kWmTmemEmpty);
+                ptx::tc_fence_after();
+            }
+            for (int c = 0; c < kChunks; ++c) {
+                ptx::mbar_wait(full_bar(stage), phase, p.error, kWmFull);        // query operand landed
+                ptx::mbar_wait(expd_bar(stage), phase, p.error, kWmExp);         // mask operand expanded
+                const uint32_t ready_leader = ptx::mapa(ready_bar(stage), 0);
+                if (ptx::elect_one_sync()) ptx::mbar_arrive_cluster(ready_leader);
+                __syncwarp();
                 if (rank == 0) {
-                    ptx::mbar_wait(tempty_bar, (it & 1u) ^ 1u, p.error, kWmTmemEmpty);
+                    ptx::mbar_wait(ready_bar(stage), phase, p.error, kWmReady);
                     ptx::tc_fence_after();
-                }
-                for (int c = 0; c < kChunks; ++c) {
-                    ptx::mbar_wait(full_bar(stage), phase, p.error, kWmFull);        // query operand landed
-                    ptx::mbar_wait(expd_bar(stage), phase, p.error, kWmExp);         // mask operand expanded
-                    ptx::mbar_arrive_cluster(ptx::mapa(ready_bar(stage), 0));
-                    if (rank == 0) {
-                        ptx::mbar_wait(ready_bar(stage), phase, p.error, kWmReady);
-                        ptx::tc_fence_after();
-                        const uint32_t sbase = base + stage * kMaskStageBytes;
+                    const uint32_t sbase = base + stage * kMaskStageBytes;
+                    if (ptx::elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < kChunkK / 32; ++k) {
                             const uint32_t acc = (c | k) ? 1u : 0u;
@@ -396,8 +403,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMaskThreads, 1)
                         ptx::umma_commit_2cta(empty_bar(stage), 3);
                         if (c == kChunks - 1) ptx::umma_commit_2cta(tfull_bar, 3);
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    __syncwarp();
                 }
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp >= 6) {

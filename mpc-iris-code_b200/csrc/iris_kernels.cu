@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(out_stage_ptr + 2 * Cfg::kOutStageBytes + 8 * (3 * Cfg::kStages + 4));
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+    const int warp = ptx::warp_idx_sync();      // warp-uniform role index (see iris_ptx.cuh)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
@@ -122,19 +121,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
     const uint32_t tile_step = gridDim.x;
 
     if (warp == kProducerWarp) {
-        // ------------------------------------------------------------------ bulk-copy producer
-        if (lane == 0) {
-            const uint64_t pol_stream = ptx::policy_evict_first();
-            const uint64_t pol_keep = ptx::policy_evict_last();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step) {
-                const uint8_t* sh = S ? p.shares + (size_t)tile * kShareTileBytes : nullptr;
-                const uint8_t* mk = M ? p.masks + (size_t)tile * kMaskTileBytes : nullptr;
-                for (int c = 0; c < kChunks; ++c) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWdProducer);
-                    const uint32_t sbase = base + stage * Cfg::kStageBytes;
-                    const uint32_t fb = full_bar(stage);
+        // ------------------------------------------------------------------ bulk-copy producer (uniform flow, one
+        // elected lane issues)
+        const uint64_t pol_stream = ptx::policy_evict_first();
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step) {
+            const uint8_t* sh = S ? p.shares + (size_t)tile * kShareTileBytes : nullptr;
+            const uint8_t* mk = M ? p.masks + (size_t)tile * kMaskTileBytes : nullptr;
+            for (int c = 0; c < kChunks; ++c) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWdProducer);
+                const uint32_t sbase = base + stage * Cfg::kStageBytes;
+                const uint32_t fb = full_bar(stage);
+                if (ptx::elect_one_sync()) {
                     ptx::mbar_arrive_expect_tx(fb, Cfg::kTxBytes);
                     if (S) {
                         ptx::bulk_g2s_hint(sbase + Cfg::kOffAlo, sh + (size_t)c * kShareChunkBytes, kShareChunkBytes, fb,
@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                         ptx::bulk_g2s_hint(sbase + Cfg::kOffQm, p.qm + (size_t)c * kQmChunkBytes, kQmChunkBytes, fb,
                                            pol_keep);
                     }
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == kMmaWarp) {
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                 ptx::mbar_wait(full_bar(stage), phase, p.error, kWdMmaFull);
                 if (M) ptx::mbar_wait(expd_bar(stage), phase, p.error, kWdMmaExp);
                 ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sbase = base + stage * Cfg::kStageBytes;
+                const uint32_t sbase = base + stage * Cfg::kStageBytes;
+                if (ptx::elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < kChunkK / 32; ++k) {
                         const uint32_t acc = (c | k) ? 1u : 0u;

@@ -27,11 +27,14 @@ constexpr int kMsPkBytes = kMsSub * kMaskChunkBytes;         // 8 KiB
 constexpr int kMsQmBytes = kMsSub * kQmChunkBytes;           // 16 KiB
 constexpr int kMsStageBytes = kMsPkBytes + kMsQmBytes;       // 24 KiB
 constexpr int kMsStages = 8;
-constexpr int kMsARing = 3;                                  // TMEM A stages (128 columns each)
+constexpr int kMsARing = 2;                                  // TMEM A stages (128 columns each)
+constexpr int kMsAccSplit = 4;                               // independent accumulators (one per K step): an N=32
+                                                             // UMMA is ~16 cycles of work but ~100 cycles deep, so
+                                                             // back-to-back accumulation into ONE tile serialises
 constexpr int kMsOutStageBytes = 8192;
 constexpr int kMsSmemBytes = 1024 + kMsStages * kMsStageBytes + kMsOutStageBytes + 512;
 constexpr int kMsThreads = 320;
-constexpr uint32_t kMsAccCols = 64;                          // 2 accumulator buffers x 32 columns
+constexpr uint32_t kMsAccCols = 2 * kMsAccSplit * 32;        // 2 accumulator buffers x 4 partial tiles x 32 columns
 constexpr uint32_t kMsTmemCols = 512;
 static_assert(kChunks % kMsSub == 0, "stages must tile the K dimension");
 static_assert(kMsAccCols + kMsARing * 128 <= kMsTmemCols, "TMEM budget");
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
         out_stage_ptr + kMsOutStageBytes + 8 * (2 * kMsStages + 2 * kMsARing + 4));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = ptx::warp_idx_sync();      // warp-uniform role index
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -125,57 +128,60 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
     const uint32_t tile_step = gridDim.x;
 
     if (warp == 4) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const uint64_t pol_stream = ptx::policy_evict_first();
-            const uint64_t pol_keep = ptx::policy_evict_last();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step) {
-                const uint8_t* mk = p.masks + (size_t)tile * kMaskTileBytes;
-                for (int c = 0; c < kMsStagesPerTile; ++c) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWsProducer);
-                    const uint32_t sbase = base + stage * kMsStageBytes;
-                    const uint32_t fb = full_bar(stage);
+        // ------------------------------------------------------------------ producer (whole warp in uniform flow,
+        // one elected lane issues: operands stay in uniform registers)
+        const uint64_t pol_stream = ptx::policy_evict_first();
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step) {
+            const uint8_t* mk = p.masks + (size_t)tile * kMaskTileBytes;
+            for (int c = 0; c < kMsStagesPerTile; ++c) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWsProducer);
+                const uint32_t sbase = base + stage * kMsStageBytes;
+                const uint32_t fb = full_bar(stage);
+                if (ptx::elect_one_sync()) {
                     ptx::mbar_arrive_expect_tx(fb, kMsStageBytes);
                     ptx::bulk_g2s_hint(sbase, mk + (size_t)c * kMsPkBytes, kMsPkBytes, fb, pol_stream);
                     ptx::bulk_g2s_hint(sbase + kMsPkBytes, p.qm + (size_t)c * kMsQmBytes, kMsQmBytes, fb, pol_keep);
-                    if (++stage == kMsStages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == kMsStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------------ UMMA issuer (A from TMEM, B from smem)
-        if (lane == 0) {
-            constexpr uint32_t kIdesc32 = ptx::umma_idesc_i8(32);
-            int stage = 0, ar = 0;
-            uint32_t phase = 0, aphase = 0, it = 0;
-            for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step, ++it) {
-                const uint32_t buf = it & 1u;
-                ptx::mbar_wait(tempty_bar(buf), ((it >> 1) & 1u) ^ 1u, p.error, kWsMmaTmem);
+        constexpr uint32_t kIdesc32 = ptx::umma_idesc_i8(32);
+        int stage = 0, ar = 0;
+        uint32_t phase = 0, aphase = 0, it = 0;
+        for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step, ++it) {
+            const uint32_t buf = it & 1u;
+            ptx::mbar_wait(tempty_bar(buf), ((it >> 1) & 1u) ^ 1u, p.error, kWsMmaTmem);
+            ptx::tc_fence_after();
+            const uint32_t d = tmem_base + buf * (kMsAccSplit * 32u);
+            for (int c = 0; c < kMsStagesPerTile; ++c) {
+                ptx::mbar_wait(full_bar(stage), phase, p.error, kWsMmaFull);
+                ptx::mbar_wait(afull_bar(ar), aphase, p.error, kWsMmaA);
                 ptx::tc_fence_after();
-                const uint32_t d = tmem_base + buf * 32u;
-                for (int c = 0; c < kMsStagesPerTile; ++c) {
-                    ptx::mbar_wait(full_bar(stage), phase, p.error, kWsMmaFull);
-                    ptx::mbar_wait(afull_bar(ar), aphase, p.error, kWsMmaA);
-                    ptx::tc_fence_after();
-                    const uint32_t qbase = base + stage * kMsStageBytes + kMsPkBytes;
-                    const uint32_t abase = tmem_base + kMsAccCols + ar * 128u;
+                const uint32_t qbase = base + stage * kMsStageBytes + kMsPkBytes;
+                const uint32_t abase = tmem_base + kMsAccCols + ar * 128u;
+                if (ptx::elect_one_sync()) {
 #pragma unroll
                     for (int sub = 0; sub < kMsSub; ++sub) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_i8_ts(d, abase + sub * 32 + k * 8,
+                            umma_i8_ts(d + k * 32, abase + sub * 32 + k * 8,
                                        ptx::umma_desc_sw128(qbase + sub * kQmChunkBytes + 32 * k), kIdesc32,
-                                       (c | sub | k) ? 1u : 0u);
+                                       (c | sub) ? 1u : 0u);   // K step k accumulates into partial tile k
                         }
                     }
                     ptx::umma_commit(aempty_bar(ar));
                     ptx::umma_commit(empty_bar(stage));
                     if (c == kMsStagesPerTile - 1) ptx::umma_commit(tfull_bar(buf));
-                    if (++stage == kMsStages) { stage = 0; phase ^= 1u; }
-                    if (++ar == kMsARing) { ar = 0; aphase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == kMsStages) { stage = 0; phase ^= 1u; }
+                if (++ar == kMsARing) { ar = 0; aphase ^= 1u; }
             }
         }
     } else if (warp >= 6) {
@@ -222,15 +228,23 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
             const uint32_t buf = it & 1u;
             ptx::mbar_wait(tfull_bar(buf), (it >> 1) & 1u, p.error, kWsEpilogue);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 32u;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (kMsAccSplit * 32u);
             const int64_t trow0 = (int64_t)tile * kTileRows;
             int64_t lo = (int64_t)p.row_begin - trow0, hi = (int64_t)p.row_end - trow0;
             const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
             const int r1 = (int)(hi < 0 ? 0 : (hi > kTileRows ? kTileRows : hi));
             const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
             uint32_t a[32];
-            ptx::tmem_ld32(taddr, a);
-            ptx::tmem_wait_ld();
+            {
+                uint32_t b[32], c2[32], d2[32];
+                ptx::tmem_ld32(taddr, a);
+                ptx::tmem_ld32(taddr + 32, b);
+                ptx::tmem_ld32(taddr + 64, c2);
+                ptx::tmem_ld32(taddr + 96, d2);
+                ptx::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] += b[j] + c2[j] + d2[j];   // sum of the 4 partial tiles
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));

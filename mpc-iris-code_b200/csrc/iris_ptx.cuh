@@ -11,6 +11,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- warp-uniform role dispatch
+// The single-thread instructions of this file (tcgen05.mma / commit, cp.async.bulk) take their operands from
+// UNIFORM registers.  If they sit in a `lane == 0` branch the compiler must assume divergent values and wraps
+// every one of them in an ELECT / R2UR.BROADCAST waterfall loop (~100 cycles per UMMA).  Keeping the whole warp
+// in uniform control flow (warp index via shuffle) and predicating only the instruction itself with elect.sync
+// lets the descriptors live in uniform registers.
+__device__ __forceinline__ int warp_idx_sync() {
+    return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+}
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
