@@ -33,7 +33,8 @@ constexpr int kMsAccSplit = 4;                               // independent accu
                                                              // back-to-back accumulation into ONE tile serialises
 constexpr int kMsOutStageBytes = 8192;
 constexpr int kMsSmemBytes = 1024 + kMsStages * kMsStageBytes + kMsOutStageBytes + 512;
-constexpr int kMsThreads = 320;
+constexpr int kMsExpWarps = 8;                               // 2 per TMEM lane quadrant, each expands half a stage
+constexpr int kMsThreads = (6 + kMsExpWarps) * 32;
 constexpr uint32_t kMsAccCols = 2 * kMsAccSplit * 32;        // 2 accumulator buffers x 4 partial tiles x 32 columns
 constexpr uint32_t kMsTmemCols = 512;
 static_assert(kChunks % kMsSub == 0, "stages must tile the K dimension");
@@ -56,16 +57,19 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 __device__ __forceinline__ void tmem_wait_st() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]   (TS form)
-__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]   (TS form).  The B descriptor is passed as (lo, hi) words so that stepping
+// through a stage is ONE uniform add per operand instead of rebuilding the 64-bit descriptor per instruction.
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
 
 __device__ __forceinline__ void ms_copy_out(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
     if (b1 <= b0) return;
@@ -91,8 +95,8 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
     uint8_t* const out_stage_ptr = base_ptr + kMsStages * kMsStageBytes;
     const uint32_t bars = base + kMsStages * kMsStageBytes + kMsOutStageBytes;
     auto full_bar = [&](int s) { return bars + 8u * s; };                          // smem stage landed
-    auto empty_bar = [&](int s) { return bars + 8u * (kMsStages + s); };           // count 5: 4 expander warps + UMMA commit
-    auto afull_bar = [&](int a) { return bars + 8u * (2 * kMsStages + a); };       // TMEM A stage written (4 warps)
+    auto empty_bar = [&](int s) { return bars + 8u * (kMsStages + s); };           // count: expander warps + UMMA commit
+    auto afull_bar = [&](int a) { return bars + 8u * (2 * kMsStages + a); };       // TMEM A stage written (all expander warps)
     auto aempty_bar = [&](int a) { return bars + 8u * (2 * kMsStages + kMsARing + a); };   // UMMA done reading it
     auto tfull_bar = [&](int b) { return bars + 8u * (2 * kMsStages + 2 * kMsARing + b); };
     auto tempty_bar = [&](int b) { return bars + 8u * (2 * kMsStages + 2 * kMsARing + 2 + b); };
@@ -106,10 +110,10 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMsStages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), 5);
+            ptx::mbar_init(empty_bar(s), kMsExpWarps + 1);
         }
         for (int a = 0; a < kMsARing; ++a) {
-            ptx::mbar_init(afull_bar(a), 4);
+            ptx::mbar_init(afull_bar(a), kMsExpWarps);
             ptx::mbar_init(aempty_bar(a), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -165,14 +169,15 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
                 ptx::tc_fence_after();
                 const uint32_t qbase = base + stage * kMsStageBytes + kMsPkBytes;
                 const uint32_t abase = tmem_base + kMsAccCols + ar * 128u;
+                const uint32_t blo0 = ((qbase & 0x3FFFFu) >> 4) | (1u << 16);
                 if (ptx::elect_one_sync()) {
 #pragma unroll
                     for (int sub = 0; sub < kMsSub; ++sub) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_i8_ts(d + k * 32, abase + sub * 32 + k * 8,
-                                       ptx::umma_desc_sw128(qbase + sub * kQmChunkBytes + 32 * k), kIdesc32,
-                                       (c | sub) ? 1u : 0u);   // K step k accumulates into partial tile k
+                            // K step k accumulates into partial tile k
+                            umma_i8_ts(d + k * 32, abase + sub * 32 + k * 8, blo0 + ((sub * kQmChunkBytes + 32 * k) >> 4),
+                                       kDescHiSw128, kIdesc32, sub ? 1u : (c ? 1u : 0u));
                         }
                     }
                     ptx::umma_commit(aempty_bar(ar));
@@ -187,6 +192,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
     } else if (warp >= 6) {
         // ------------------------------------------------------------------ expanders: packed bits -> TMEM A operand
         const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int half = (warp - 6) >> 2;                 // which half of the stage's 128-bit chunks this warp expands
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         int stage = 0, ar = 0;
@@ -199,7 +205,8 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
                 const uint8_t* pk = base_ptr + stage * kMsStageBytes;
                 const uint32_t abase = tmem_base + lane_addr + kMsAccCols + ar * 128u;
 #pragma unroll
-                for (int sub = 0; sub < kMsSub; ++sub) {
+                for (int s2 = 0; s2 < kMsSub / 2; ++s2) {
+                    const int sub = half * (kMsSub / 2) + s2;
                     const uint4 x = *reinterpret_cast<const uint4*>(pk + sub * kMaskChunkBytes + row * 16);
                     const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
                     uint32_t v[32];
