@@ -1,0 +1,51 @@
+"""Launches every product kernel a few times at bench-like sizes; the command ncu is pointed at for profiles/.
+
+    python tools/profile_all.py [rows] [batch_rows]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mpc_iris_code_b200 as iris  # noqa: E402
+import oracle as O  # noqa: E402
+
+
+def main():
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+    brows = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000
+    db = iris.Database(rows)
+    db.generate(0x1715C0DE, 0, rows)
+    qm = O.gen_mask_rows(5, 1, 1)[0]
+    q = O.encode(O.gen_mask_rows(5, 0, 1)[0], qm)
+    de, me = iris.DistanceEngine(q), iris.MasksEngine(qm)
+    dist = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
+    den = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
+    for _ in range(3):
+        iris.match(de, me, db, 0, rows, dist, den)         # scan_kernel<1,1>
+    for _ in range(3):
+        iris.match(de, None, db, 0, rows, dist, None)      # scan_kernel<1,0>
+    for _ in range(3):
+        iris.match(None, me, db, 0, rows, None, den)       # mask_scan_kernel
+    db.synchronize()
+    nq = 64
+    big = torch.empty((nq, brows, 31), dtype=torch.int16, device="cuda")
+    tern = [iris.DistanceEngine(O.encode(O.gen_mask_rows(100 + i, 0, 1)[0], O.gen_mask_rows(100 + i, 1, 1)[0])) for i in range(nq)]
+    unif = [iris.DistanceEngine(O.gen_share_rows(200 + i, 0, 1)[0]) for i in range(nq)]
+    mes = [iris.MasksEngine(O.gen_mask_rows(100 + i, 1, 1)[0]) for i in range(nq)]
+    for _ in range(3):
+        iris.distances_batch(tern, db, 0, brows, big)      # batch_distances_kernel<1>
+    for _ in range(3):
+        iris.distances_batch(unif, db, 0, brows, big)      # batch_distances_kernel<0>
+    for _ in range(3):
+        iris.denominators_batch(mes, db, 0, brows, big)    # batch_denominators_kernel
+    db.synchronize()
+    print("min/argmin:", iris.match_min(de, me, db, 0, rows))   # scan + combine_decode + final_min
+    print("launches:", iris.launch_count())
+
+
+if __name__ == "__main__":
+    main()
