@@ -379,6 +379,30 @@ def run_b200(args):
         ok &= np.array_equal(hd_np[i], O.distance_batch(q, O.gen_share_rows(SEED, rank * rows + int(i), 1))[0])
         ok &= np.array_equal(hn_np[i], O.masks_batch(qm, O.gen_mask_rows(SEED, rank * rows + int(i), 1))[0])
 
+    # ---- sharded search with a small-vector gather (all ranks): per step the query goes host->device, every rank
+    # scans and REDUCES its shard on the device (decode_distance + min/argmin, 16 bytes back), and the per-shard
+    # (min, argmin) pairs are all-gathered over NCCL -- the only collective of the multi-GPU path.
+    from mpc_iris_code_b200.sharding import gather_best
+
+    def search_step():
+        e1, e2 = iris.DistanceEngine(q_np, device=local_rank), iris.MasksEngine(qm_np, device=local_rank)
+        md, mi = iris.match_min(e1, e2, db, 0, rows, index_base=rank * rows)
+        best = gather_best(md, mi - rank * rows if mi >= 0 else -1, rank * rows)
+        e1.close()
+        e2.close()
+        return best
+
+    for _ in range(3):
+        search_step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        best = search_step()
+    torch.cuda.synchronize()
+    search_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -414,6 +438,13 @@ def run_b200(args):
                 "path": "DistanceEngine::new + MasksEngine::new + fused batch_process on the resident shard, pinned host buffers"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
+    }
+    line["sharded_search"] = {
+        "comparisons_per_s": rows * world * e2e_steps / search_s, "ms_per_query": search_s / e2e_steps * 1e3,
+        "h2d_bytes_per_step": 25600 + 1600, "d2h_bytes_per_step": 16,
+        "collective": "all_gather of each shard's (min distance, argmin) over NCCL" if world > 1 else "none (one shard)",
+        "path": "engines from host query + iris_match_min_resident (scan + decode_distance + argmin on device) + gather_best",
+        "result": [best[0], best[1]],
     }
     if world == 1 and not args.no_extras:
         try:
