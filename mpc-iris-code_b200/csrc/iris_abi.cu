@@ -382,7 +382,7 @@ static int ensure_result_buffers(iris_db* db, uint64_t rows) {
 
 // qd / qm: prepared operand images (nullptr = that half is not computed).
 static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t row_begin, uint64_t row_end,
-                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev) {
+                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev, bool signed_query = false) {
     if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
     if (!qd && !qm) return fail(IRIS_ERR_INVALID, "no engine given");
     if (row_begin > row_end) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
@@ -406,6 +406,7 @@ static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t
     p.qm = qm;
     p.raw_out = raw_dev;
     p.error = db->d_error;
+    p.signed_query = signed_query && !raw_dev;   // the raw dump shows the three-product accumulators
 
     const bool dist_dev = !qd || is_device_pointer(dist_out);
     const bool den_dev = !qm || is_device_pointer(den_out);
@@ -645,7 +646,7 @@ extern "C" int iris_distance_engine_batch_process(iris_distance_engine* e, uint1
         iris_db_clear(e->scratch);
         int rc = iris_db_append_shares(e->scratch, db + off * IRIS_BITS, m);
         if (rc) return rc;
-        rc = scan_core(e->scratch, e->d_qd, nullptr, 0, m, out + off * IRIS_ROTATIONS, nullptr, nullptr);
+        rc = scan_core(e->scratch, e->d_qd, nullptr, 0, m, out + off * IRIS_ROTATIONS, nullptr, nullptr, e->fits_s8);
         if (rc) return rc;
         rc = iris_db_synchronize(e->scratch);
         if (rc) return rc;
@@ -684,7 +685,7 @@ extern "C" int iris_distance_engine_batch_process_resident(iris_distance_engine*
     if (e->device != db->device) return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
     if (row_end < row_begin || out_len != row_end - row_begin)
         return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)(row_end - row_begin));
-    return scan_core(db, e->d_qd, nullptr, row_begin, row_end, out, nullptr, nullptr);
+    return scan_core(db, e->d_qd, nullptr, row_begin, row_end, out, nullptr, nullptr, e->fits_s8);
 }
 
 extern "C" int iris_masks_engine_batch_process_resident(iris_masks_engine* e, uint16_t* out, uint64_t out_len,
@@ -702,7 +703,7 @@ extern "C" int iris_match_resident(iris_distance_engine* de, iris_masks_engine* 
     if ((de && de->device != db->device) || (me && me->device != db->device))
         return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
     return scan_core(db, de ? de->d_qd : nullptr, me ? me->d_qm : nullptr, row_begin, row_end, distances_out,
-                     denominators_out, nullptr);
+                     denominators_out, nullptr, de && de->fits_s8);
 }
 
 extern "C" int iris_distances(int device, const uint16_t* query, const uint16_t* entry, uint16_t* out) {
@@ -991,7 +992,7 @@ extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engi
     uint8_t* scratch = db->d_red + 2 * row_bytes;
     void* result = scratch + (combine_scratch_bytes(n) / 16) * 16 + 16;
     if (n) {
-        int rc = scan_core(db, de->d_qd, me->d_qm, row_begin, row_end, d_dist, d_den, nullptr);
+        int rc = scan_core(db, de->d_qd, me->d_qm, row_begin, row_end, d_dist, d_den, nullptr, de->fits_s8);
         if (rc) return rc;
     }
     CombineParams p{};

@@ -29,19 +29,22 @@ void count_launch_external() { count_launch(); }
 // =====================================================================================
 // scan kernel
 // =====================================================================================
-template <bool S, bool M>
+// SQ: every query element is a sign-extended byte (true for encode() output): the q_lo plane read as s8 IS the
+// value, so the q_hi plane is neither loaded nor multiplied (two limb products instead of three).
+template <bool S, bool M, bool SQ>
 struct ScanCfg {
     static constexpr int kOffAlo = 0;
     static constexpr int kOffAhi = kPlaneTileBytes;
     static constexpr int kOffQd = kShareChunkBytes;
-    static constexpr int kShareBytes = S ? kShareChunkBytes + kQdChunkBytes : 0;
+    static constexpr int kQdLoadBytes = SQ ? kQTileBytes : kQdChunkBytes;
+    static constexpr int kShareBytes = S ? kShareChunkBytes + kQdLoadBytes : 0;
     static constexpr int kOffAmx = kShareBytes;                  // expanded mask operand (written by SM)
     static constexpr int kOffQm = kOffAmx + kPlaneTileBytes;
     static constexpr int kOffPk = kOffQm + kQmChunkBytes;        // packed mask bytes (bulk-copied)
     static constexpr int kStageBytes = kShareBytes + (M ? kPlaneTileBytes + kQmChunkBytes + kMaskChunkBytes : 0);
     static constexpr int kStages = (S && M) ? 3 : (S ? 5 : 8);
     static constexpr uint32_t kTxBytes =
-        (S ? kShareChunkBytes + kQdChunkBytes : 0) + (M ? kQmChunkBytes + kMaskChunkBytes : 0);
+        (S ? kShareChunkBytes + kQdLoadBytes : 0) + (M ? kQmChunkBytes + kMaskChunkBytes : 0);
     static constexpr int kOutStageBytes = 8192;                  // 128*62 + alignment slack
     static constexpr int kBarBytes = 512;
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kOutStageBytes + kBarBytes;
@@ -77,9 +80,9 @@ __device__ __forceinline__ void copy_out(const uint8_t* stage, uint8_t* gbase, i
         *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
 }
 
-template <bool S, bool M>
+template <bool S, bool M, bool SQ>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams p) {
-    using Cfg = ScanCfg<S, M>;
+    using Cfg = ScanCfg<S, M, SQ>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;          // shared-window address, 1024-aligned
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                     if (S) {
                         ptx::bulk_g2s_hint(sbase + Cfg::kOffAlo, sh + (size_t)c * kShareChunkBytes, kShareChunkBytes, fb,
                                            pol_stream);
-                        ptx::bulk_g2s_hint(sbase + Cfg::kOffQd, p.qd + (size_t)c * kQdChunkBytes, kQdChunkBytes, fb,
+                        ptx::bulk_g2s_hint(sbase + Cfg::kOffQd, p.qd + (size_t)c * kQdChunkBytes, Cfg::kQdLoadBytes, fb,
                                            pol_keep);
                     }
                     if (M) {
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
         // ------------------------------------------------------------------ UMMA issuer
         constexpr uint32_t kIdesc64 = ptx::umma_idesc_i8(64);
         constexpr uint32_t kIdesc32 = ptx::umma_idesc_i8(32);
+        constexpr uint32_t kIdesc32S = ptx::umma_idesc_i8(32, false, true);   // B read as s8
         int stage = 0;
         uint32_t phase = 0;
         uint32_t it = 0;
@@ -176,8 +180,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
                         const uint32_t acc = (c | k) ? 1u : 0u;
                         if (S) {
                             const uint64_t bq = ptx::umma_desc_sw128(sbase + Cfg::kOffQd + 32 * k);
-                            ptx::umma_i8(d + 0, ptx::umma_desc_sw128(sbase + Cfg::kOffAlo + 32 * k), bq, kIdesc64, acc);
-                            ptx::umma_i8(d + 64, ptx::umma_desc_sw128(sbase + Cfg::kOffAhi + 32 * k), bq, kIdesc32, acc);
+                            ptx::umma_i8(d + 0, ptx::umma_desc_sw128(sbase + Cfg::kOffAlo + 32 * k), bq,
+                                         SQ ? kIdesc32S : kIdesc64, acc);
+                            ptx::umma_i8(d + 64, ptx::umma_desc_sw128(sbase + Cfg::kOffAhi + 32 * k), bq,
+                                         SQ ? kIdesc32S : kIdesc32, acc);
                         }
                         if (M) {
                             ptx::umma_i8(d + 96, ptx::umma_desc_sw128(sbase + Cfg::kOffAmx + 32 * k),
@@ -240,7 +246,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
             if (S) {
                 uint32_t b[32], c2[32];
                 ptx::tmem_ld32(taddr + 0, a);
-                ptx::tmem_ld32(taddr + 32, b);
+                if (SQ) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) b[j] = 0;    // no q_hi product on the signed path
+                } else {
+                    ptx::tmem_ld32(taddr + 32, b);
+                }
                 ptx::tmem_ld32(taddr + 64, c2);
                 ptx::tmem_wait_ld();
                 if (p.raw_out) {
@@ -291,30 +302,32 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
     if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <bool S, bool M>
+template <bool S, bool M, bool SQ>
 static cudaError_t launch_scan_t(const ScanParams& p, int num_sms, cudaStream_t stream) {
-    using Cfg = ScanCfg<S, M>;
+    using Cfg = ScanCfg<S, M, SQ>;
     static bool configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(scan_kernel<S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        e = cudaFuncSetAttribute(scan_kernel<S, M, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     const uint32_t tiles = p.tile_end - p.tile_begin;
     if (tiles == 0) return cudaSuccess;
     const uint32_t grid = tiles < (uint32_t)num_sms ? tiles : (uint32_t)num_sms;
-    scan_kernel<S, M><<<grid, kScanThreads, Cfg::kSmemBytes, stream>>>(p);
+    scan_kernel<S, M, SQ><<<grid, kScanThreads, Cfg::kSmemBytes, stream>>>(p);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
     const bool s = p.shares != nullptr, m = p.masks != nullptr;
-    if (s && m) return launch_scan_t<true, true>(p, num_sms, stream);
-    if (s) return launch_scan_t<true, false>(p, num_sms, stream);
+    if (s && m) return p.signed_query ? launch_scan_t<true, true, true>(p, num_sms, stream)
+                                      : launch_scan_t<true, true, false>(p, num_sms, stream);
+    if (s) return p.signed_query ? launch_scan_t<true, false, true>(p, num_sms, stream)
+                                 : launch_scan_t<true, false, false>(p, num_sms, stream);
     if (m) {
         // denominators only: the TMEM-operand kernel (iris_maskscan.cu); IRIS_MASKSCAN=smem selects the
         // shared-memory-operand variant of this file (kept for A/B measurements and the raw debug dump)
@@ -323,7 +336,7 @@ cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
             return e && e[0] == 's';
         }();
         if (!use_smem && !p.raw_out) return launch_mask_scan(p, num_sms, stream);
-        return launch_scan_t<false, true>(p, num_sms, stream);
+        return launch_scan_t<false, true, false>(p, num_sms, stream);
     }
     return cudaErrorInvalidValue;
 }
