@@ -286,6 +286,16 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        try:
+            # run this rank (and first-touch its pinned buffers) on the CPUs / NUMA node next to its GPU;
+            # only for N > 1 -- at N = 1 the cpu_baseline leg needs every host core
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(nvml_index(local_rank)))
+        except Exception:  # noqa: BLE001
+            pass
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
