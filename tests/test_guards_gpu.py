@@ -68,6 +68,32 @@ def test_scan_kernels_stay_inside_their_output(ctx, off, rb, re):
     _check(bn, off, m, exp_n)
 
 
+def test_batched_kernels_more_queries_than_one_launch_and_tiny_shard(ctx):
+    """70 queries span two launches (64 + 6); a 1-row shard exercises the zero-filled pair tile."""
+    iris, torch, db, shares, masks, n = ctx
+    nq = 70
+    qs = [O.gen_share_rows(500 + i, 0, 1)[0] if i % 9 == 0 else O.encode(O.gen_mask_rows(500 + i, 0, 1)[0], O.gen_mask_rows(500 + i, 1, 1)[0])
+          for i in range(nq)]
+    qms = [O.gen_mask_rows(500 + i, 1, 1)[0] for i in range(nq)]
+    rb, re = 100, 420
+    out = np.zeros((nq, re - rb, 31), np.uint16)
+    iris.distances_batch([iris.DistanceEngine(q) for q in qs], db, rb, re, out)
+    assert np.array_equal(out, np.stack([O.distance_batch(q, shares[rb:re], threads=8) for q in qs]))
+    iris.denominators_batch([iris.MasksEngine(q) for q in qms], db, rb, re, out)
+    assert np.array_equal(out, np.stack([O.masks_batch(q, masks[rb:re], threads=8) for q in qms]))
+    with iris.Database(1) as tiny:
+        tiny.append_shares(shares[:1])
+        tiny.append_masks(masks[:1])
+        o1 = np.zeros((3, 1, 31), np.uint16)
+        iris.distances_batch([iris.DistanceEngine(q) for q in qs[:3]], tiny, 0, 1, o1)
+        assert np.array_equal(o1[:, 0], np.stack([O.distances(q, shares[0]) for q in qs[:3]]))
+        iris.denominators_batch([iris.MasksEngine(q) for q in qms[:3]], tiny, 0, 1, o1)
+        assert np.array_equal(o1[:, 0], np.stack([O.denominators(q, masks[0]) for q in qms[:3]]))
+        d, dn = np.zeros((1, 31), np.uint16), np.zeros((1, 31), np.uint16)
+        iris.match(iris.DistanceEngine(qs[1]), iris.MasksEngine(qms[1]), tiny, 0, 1, d, dn)
+        assert np.array_equal(d[0], O.distances(qs[1], shares[0])) and np.array_equal(dn[0], O.denominators(qms[1], masks[0]))
+
+
 @pytest.mark.parametrize("off", [0, 3, 8])
 @pytest.mark.parametrize("rb,re", [(0, 777), (130, 700)])
 def test_batched_kernels_stay_inside_their_output(ctx, off, rb, re):
