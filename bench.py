@@ -424,6 +424,53 @@ def run_b200(args):
     search_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
 
+    # ---- BASELINE configs[3]/[4] shape on every rank: a batch of 64 queries against this rank's shard as dense int8
+    # GEMMs (distances + denominators), per-query reduction on the device, and ONE all-gather of 64 x 16 bytes.
+    batched = None
+    if not args.no_extras:
+        try:
+            from mpc_iris_code_b200.sharding import gather_best_batch
+
+            nq = 64
+            tq = [(O.gen_mask_rows(9000 + i, 0, 1)[0], O.gen_mask_rows(9000 + i, 1, 1)[0]) for i in range(nq)]
+            bd = torch.empty((nq, rows, 31), dtype=torch.int16, device="cuda")
+            bn = torch.empty((nq, rows, 31), dtype=torch.int16, device="cuda")
+
+            def batch_step():
+                des = [iris.DistanceEngine.from_template(p_, m_, device=local_rank) for p_, m_ in tq]   # 3 200 B each, H2D
+                mes = [iris.MasksEngine(m_, device=local_rank) for _, m_ in tq]
+                iris.distances_batch(des, db, 0, rows, bd)
+                iris.denominators_batch(mes, db, 0, rows, bn)
+                db.synchronize()
+                mins, idxs = iris.combine_min_batch(bd, bn, nq, index_base=rank * rows, device=local_rank)
+                res = gather_best_batch(mins, idxs)
+                for e_ in des + mes:
+                    e_.close()
+                return res
+
+            batch_step()
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            bsteps = 3
+            for _ in range(bsteps):
+                bres = batch_step()
+            torch.cuda.synchronize()
+            bs = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            batched = {
+                "queries": nq, "rows_per_gpu": rows, "ms_per_batch": bs / bsteps * 1e3,
+                "comparisons_per_s": nq * rows * world * bsteps / bs,
+                "h2d_bytes_per_step": nq * 3200, "d2h_bytes_per_step": nq * 16,
+                "collective": "all_gather of 64 x (min distance, argmin) per shard over NCCL" if world > 1 else "none (one shard)",
+                "path": "64 x DistanceEngine.from_template + MasksEngine, batched int8-GEMM distances + denominators, "
+                        "iris_combine_min_batch on device, gather_best_batch",
+                "first_result": [float(bres[0][0]), int(bres[1][0])],
+            }
+            del bd, bn
+        except Exception as ex:  # noqa: BLE001
+            batched = {"error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -467,6 +514,8 @@ def run_b200(args):
         "path": "engines from host query + iris_match_min_resident (scan + decode_distance + argmin on device) + gather_best",
         "result": [best[0], best[1]],
     }
+    if batched is not None:
+        line["batched_search_64q"] = batched
     if world == 1 and not args.no_extras:
         try:
             line["extras"] = secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den)

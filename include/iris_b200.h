@@ -145,6 +145,10 @@ int iris_denominators_batch_resident(iris_masks_engine *const *engines, uint32_t
 int iris_combine_min(int device, const uint16_t *const *distance_shares, uint32_t parties,
                      const uint16_t *denominators, uint64_t n, uint64_t index_base, double *distances_out,
                      double *min_distance, uint64_t *min_index);
+/* The same reduction for a whole batch: distances / denominators are [Q][n][31] DEVICE arrays as written by the
+ * batched kernels (synchronise the producing shard first); min_distance / min_index receive Q entries. */
+int iris_combine_min_batch(int device, const uint16_t *distances, const uint16_t *denominators, uint32_t num_queries,
+                           uint64_t n, uint64_t index_base, double *min_distance, uint64_t *min_index);
 /* Fused scan + reduction for a shard that holds the whole (1-share) encodings: both engines over rows
  * [row_begin,row_end), decode and min/argmin on the device; only 16 bytes return to the host.  This is
  * the per-shard step of the multi-GPU path (each rank reduces its rows, the pairs are all-gathered). */

@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     IrisError,
     MasksEngine,
     combine_min,
+    combine_min_batch,
     match_min,
     denominators,
     denominators_batch,

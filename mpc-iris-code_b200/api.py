@@ -81,6 +81,7 @@ def lib():
         "iris_denominators_batch_resident": [vp, u32, vp, u64, u64, vp],
         "iris_combine_min": [i32, vp, u32, vp, u64, u64, vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
         "iris_match_min_resident": [vp, vp, vp, u64, u64, u64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
+        "iris_combine_min_batch": [i32, vp, vp, u32, u64, u64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
         "iris_distances": [i32, vp, vp, vp],
         "iris_denominators": [i32, vp, vp, vp],
         "iris_check_distances_simt": [vp, vp, u64, u64, vp],
@@ -397,6 +398,17 @@ def combine_min(distance_shares, denominators, index_base: int = 0, device: int 
                                   ctypes.byref(md), ctypes.byref(mi)))
     idx = -1 if mi.value == 2**64 - 1 else mi.value
     return (md.value, idx, dist) if want_distances else (md.value, idx)
+
+
+def combine_min_batch(distances, denominators, num_queries: int, index_base: int = 0, device: int = 0):
+    """Per-query (min distance, argmin) over [Q][n][31] device arrays produced by the batched kernels."""
+    n = _numel(denominators) // (ROTATIONS * num_queries)
+    md = (ctypes.c_double * num_queries)()
+    mi = (ctypes.c_uint64 * num_queries)()
+    _check(lib().iris_combine_min_batch(device, _ptr(distances, np.uint16, num_queries * n * ROTATIONS, "distances"),
+                                        _ptr(denominators, np.uint16, num_queries * n * ROTATIONS, "denominators"),
+                                        num_queries, n, index_base, md, mi))
+    return np.array(md[:], np.float64), np.array([-1 if v == 2**64 - 1 else v for v in mi[:]], np.int64)
 
 
 def match_min(distance_engine: DistanceEngine, masks_engine: MasksEngine, db: Database, row_begin: int, row_end: int,

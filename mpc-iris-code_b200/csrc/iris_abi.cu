@@ -970,6 +970,46 @@ extern "C" int iris_combine_min(int device, const uint16_t* const* distance_shar
     return rc;
 }
 
+// Reduction of a whole batch: distances / denominators are [Q][n][31] DEVICE arrays (the outputs of the batched
+// kernels); one (min, argmin) pair per query comes back.  One scratch allocation, 2Q launches, one sync.
+extern "C" int iris_combine_min_batch(int device, const uint16_t* distances, const uint16_t* denominators,
+                                      uint32_t num_queries, uint64_t n, uint64_t index_base, double* min_distance,
+                                      uint64_t* min_index) {
+    if (!distances || !denominators || !min_distance || !min_index) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (num_queries == 0) return IRIS_OK;
+    int rc = require_device(device);
+    if (rc) return rc;
+    if (!is_device_pointer(distances) || !is_device_pointer(denominators))
+        return fail(IRIS_ERR_INVALID, "iris_combine_min_batch takes device arrays");
+    DeviceGuard g(device);
+    const size_t sbytes = (combine_scratch_bytes(n) + 15) / 16 * 16;
+    uint8_t* scratch = nullptr;
+    CK(cudaMalloc(&scratch, sbytes + 16 * (size_t)num_queries));
+    auto body = [&]() -> int {
+        for (uint32_t q = 0; q < num_queries; ++q) {
+            CombineParams p{};
+            p.shares[0] = distances + (size_t)q * n * IRIS_ROTATIONS;
+            p.parties = 1;
+            p.denominators = denominators + (size_t)q * n * IRIS_ROTATIONS;
+            p.n = n;
+            p.index_base = index_base;
+            CK(launch_combine_min(p, scratch, scratch + sbytes + 16 * (size_t)q, cudaStreamPerThread));
+        }
+        std::vector<uint64_t> host(2 * (size_t)num_queries);
+        CK(cudaMemcpyAsync(host.data(), scratch + sbytes, 16 * (size_t)num_queries, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        for (uint32_t q = 0; q < num_queries; ++q) {
+            std::memcpy(&min_distance[q], &host[2 * q], sizeof(double));
+            min_index[q] = host[2 * q + 1];
+        }
+        return IRIS_OK;
+    };
+    rc = body();
+    cudaStreamSynchronize(cudaStreamPerThread);
+    cudaFree(scratch);
+    return rc;
+}
+
 // Fused scan + reduction on a resident shard holding the full (n = 1 share) encodings: both engines over
 // rows [row_begin,row_end), then decode + min/argmin on the device; only 16 bytes come back.
 extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,

@@ -69,6 +69,23 @@ def test_batched_denominators_equal_single_query_scan_everywhere(setup):
     assert int(out.max()) <= 12800
 
 
+def test_combine_min_batch_matches_per_query_reduction(setup):
+    iris, torch, db, n = setup
+    nq, m = 9, 50_000
+    qms = [O.gen_mask_rows(7000 + i, 1, 1)[0] for i in range(nq)]
+    qs = [O.encode(O.gen_mask_rows(7000 + i, 0, 1)[0], qms[i]) for i in range(nq)]
+    d = torch.zeros((nq, m, 31), dtype=torch.int16, device="cuda")
+    dn = torch.zeros((nq, m, 31), dtype=torch.int16, device="cuda")
+    iris.distances_batch([iris.DistanceEngine(q) for q in qs], db, 1000, 1000 + m, d)
+    iris.denominators_batch([iris.MasksEngine(q) for q in qms], db, 1000, 1000 + m, dn)
+    db.synchronize()
+    mins, idxs = iris.combine_min_batch(d, dn, nq, index_base=1000)
+    hd, hn = d.cpu().numpy().view(np.uint16), dn.cpu().numpy().view(np.uint16)
+    for i in range(nq):
+        em, ei = O.combine_min(hd[i][None], hn[i])
+        assert (mins[i], idxs[i]) == (em, 1000 + ei)
+
+
 def test_match_min_at_scale_agrees_with_host_reduction(setup):
     iris, torch, db, n = setup
     qm = O.gen_mask_rows(6000, 1, 1)[0]

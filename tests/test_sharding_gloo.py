@@ -60,8 +60,14 @@ def _worker(rank, world, port, out):
     den = O.masks_batch(qm, em[b:e])
     md, mi = O.combine_min(d[None], den)
     best = gather_best(md, mi, b)
+    # batched form: three "queries" per shard -- the real one, one with no finite distance on rank 1, one all-inf
+    from mpc_iris_code_b200.sharding import gather_best_batch
+
+    mins = np.array([md, 0.25 if rank == 0 else np.inf, np.inf])
+    idxs = np.array([b + mi if mi >= 0 else -1, b + 1 if rank == 0 else -1, -1], np.int64)
+    bm, bi = gather_best_batch(mins, idxs)
     if rank == 0:
-        out.put((best, (b, e)))
+        out.put((best, (b, e), bm.tolist(), bi.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,10 +83,11 @@ def test_two_rank_gather_matches_unsharded():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    best, _ = out.get(timeout=120)
+    best, _, bm, bi = out.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     q, qm, enc, em = _problem()
     md, mi = O.combine_min(O.distance_batch(q, enc)[None], O.masks_batch(qm, em))
     assert best == (md, mi) == (0.0, 3)
+    assert bm == [0.0, 0.25, float("inf")] and bi == [3, 1, -1]
