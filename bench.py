@@ -204,18 +204,34 @@ def nvml_index(local_rank: int) -> int:
 
 
 # ----------------------------------------------------------------------------------- secondary configs
-def _time_ms(stream, fn, sync, warmup=2, iters=5):
+_NVML = {"nv": None, "h": None, "last_mhz": None}
+
+
+def _time_ms(stream, fn, sync, warmup=2, iters=5, cool_s=0.0):
+    """Mean device time of fn (CUDA events on the launch stream); the SM clock is sampled while the timed launches
+    run (the 1 kW cap moves it between ~1.2 and 1.97 GHz depending on what ran before) and left in _NVML['last_mhz']."""
     import torch
 
     for _ in range(warmup):
         fn()
     sync()
+    if cool_s:
+        time.sleep(cool_s)      # let the power-averaging window recover: a burst figure, like the library GEMM's
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(stream)
     for _ in range(iters):
         fn()
     e.record(stream)
+    clk = []
+    if _NVML["h"] is not None:
+        while not e.query():
+            try:
+                clk.append(_NVML["nv"].nvmlDeviceGetClockInfo(_NVML["h"], _NVML["nv"].NVML_CLOCK_SM))
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.001)
     sync()
+    _NVML["last_mhz"] = float(np.median(clk)) if clk else None
     return s.elapsed_time(e) / iters
 
 
@@ -230,10 +246,11 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     ms = _time_ms(stream, lambda: iris.match(None, me, db, 0, rows, None, d_den), db.synchronize)
     out["denominators_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
                                    "algorithmic_GBps": rows * 1662 / (ms * 1e-3) / 1e9,
-                                   "note": "issue/latency bound, not HBM bound (DESIGN.md 5.1)"}
+                                   "sm_mhz": _NVML["last_mhz"],
+                                   "note": "bound by the UMMA operand fetch, not by HBM (DESIGN.md 5.3)"}
     ms = _time_ms(stream, lambda: iris.match(de, None, db, 0, rows, d_dist, None), db.synchronize)
     out["distances_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
-                                "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9}
+                                "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9, "sm_mhz": _NVML["last_mhz"]}
     # int8 library GEMM on this box: the measured tensor-core denominator
     a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
     b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
@@ -253,21 +270,24 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     unif = [O.gen_share_rows(8000 + i, 0, 1)[0] for i in range(nq)]
     qms = [O.gen_mask_rows(7000 + i, 1, 1)[0] for i in range(nq)]
     big = torch.empty((nq, rows, 31), dtype=torch.int16, device="cuda")
-    res = {"queries": nq, "rows": rows, "int8_library_gemm_Pops": lib_pops, "int8_nominal_Pops": 4.5}
+    res = {"queries": nq, "rows": rows, "int8_library_gemm_Pops": lib_pops, "int8_nominal_Pops": 4.5,
+           "timing": "3 launches after a 2 s pause (burst, like the 20-launch library GEMM); sm_mhz = median SM clock "
+                     "while they ran; back to back for seconds the 1 kW cap pulls the clock to ~1.2-1.5 GHz"}
     for name, qs, prods in (("ternary", tern, 2), ("uniform_u16", unif, 3)):
         eng = [iris.DistanceEngine(x) for x in qs]
-        ms = _time_ms(stream, lambda: iris.distances_batch(eng, db, 0, rows, big), db.synchronize, warmup=1, iters=3)
+        ms = _time_ms(stream, lambda: iris.distances_batch(eng, db, 0, rows, big), db.synchronize, warmup=1, iters=3, cool_s=2.0)
         useful = 2 * rows * nq * 31 * 12800 * prods / (ms * 1e-3) / 1e15
         res[f"distances_{name}"] = {"ms": ms, "comparisons_per_s": rows * nq / (ms * 1e-3), "limb_products": prods,
                                     "useful_int8_Pops": useful, "frac_of_nominal": useful / 4.5,
-                                    "frac_of_library_gemm": useful / lib_pops}
+                                    "frac_of_library_gemm": useful / lib_pops, "sm_mhz": _NVML["last_mhz"]}
         for x in eng:
             x.close()
     eng = [iris.MasksEngine(x) for x in qms]
-    ms = _time_ms(stream, lambda: iris.denominators_batch(eng, db, 0, rows, big), db.synchronize, warmup=1, iters=3)
+    ms = _time_ms(stream, lambda: iris.denominators_batch(eng, db, 0, rows, big), db.synchronize, warmup=1, iters=3, cool_s=2.0)
     useful = 2 * rows * nq * 31 * 12800 / (ms * 1e-3) / 1e15
     res["denominators"] = {"ms": ms, "comparisons_per_s": rows * nq / (ms * 1e-3), "useful_int8_Pops": useful,
-                           "frac_of_nominal": useful / 4.5, "frac_of_library_gemm": useful / lib_pops}
+                           "frac_of_nominal": useful / 4.5, "frac_of_library_gemm": useful / lib_pops,
+                           "sm_mhz": _NVML["last_mhz"]}
     both = res["distances_ternary"]["ms"] + res["denominators"]["ms"]
     res["distances_plus_denominators_ternary"] = {"ms": both, "comparisons_per_s": rows * nq / (both * 1e-3)}
     out["batched_64q_int8_gemm"] = res
@@ -333,6 +353,8 @@ def run_b200(args):
 
     sampler = ClockSampler(nvml_index(local_rank))
     sampler.start()
+    if sampler.ok:
+        _NVML["nv"], _NVML["h"] = sampler.nv, sampler.h
 
     # ---- kernel-only: inputs resident in HBM, results stay in HBM; the database (27.2 GB at 1 M rows)
     # is far larger than L2, so every step streams from DRAM.
