@@ -454,13 +454,15 @@ def run_b200(args):
             from mpc_iris_code_b200.sharding import gather_best_batch
 
             nq = 64
-            tq = [(O.gen_mask_rows(9000 + i, 0, 1)[0], O.gen_mask_rows(9000 + i, 1, 1)[0]) for i in range(nq)]
+            tq = np.stack([np.concatenate([O.gen_mask_rows(9000 + i, 0, 1)[0], O.gen_mask_rows(9000 + i, 1, 1)[0]])
+                           for i in range(nq)])                                       # [64][400] u64 wire Templates
+            tq_pin = torch.from_numpy(tq.view(np.int64).copy()).pin_memory()
+            tq_np = tq_pin.numpy().view(np.uint64)
             bd = torch.empty((nq, rows, 31), dtype=torch.int16, device="cuda")
             bn = torch.empty((nq, rows, 31), dtype=torch.int16, device="cuda")
 
             def batch_step():
-                des = [iris.DistanceEngine.from_template(p_, m_, device=local_rank) for p_, m_ in tq]   # 3 200 B each, H2D
-                mes = [iris.MasksEngine(m_, device=local_rank) for _, m_ in tq]
+                des, mes = iris.engines_from_templates(tq_np, device=local_rank)      # 64 x 3 200 B, one H2D
                 iris.distances_batch(des, db, 0, rows, bd)
                 iris.denominators_batch(mes, db, 0, rows, bn)
                 db.synchronize()
@@ -485,7 +487,7 @@ def run_b200(args):
                 "comparisons_per_s": nq * rows * world * bsteps / bs,
                 "h2d_bytes_per_step": nq * 3200, "d2h_bytes_per_step": nq * 16,
                 "collective": "all_gather of 64 x (min distance, argmin) per shard over NCCL" if world > 1 else "none (one shard)",
-                "path": "64 x DistanceEngine.from_template + MasksEngine, batched int8-GEMM distances + denominators, "
+                "path": "iris_engines_new_from_templates (64 wire Templates), batched int8-GEMM distances + denominators, "
                         "iris_combine_min_batch on device, gather_best_batch",
                 "first_result": [float(bres[0][0]), int(bres[1][0])],
             }

@@ -101,6 +101,11 @@ int iris_distance_engine_new(int device, const uint16_t query[IRIS_BITS], iris_d
  * (src/lib.rs:16-26) and the rotation preparation both run on the device from the wire Template. */
 int iris_distance_engine_new_from_template(int device, const uint64_t pattern[IRIS_LIMBS],
                                            const uint64_t mask[IRIS_LIMBS], iris_distance_engine **out);
+/* The same for num_queries Templates at once (templates = [num_queries] x {pattern[200], mask[200]} u64, the wire
+ * layout of src/template.rs:26-29): fills distance_engines[i] = DistanceEngine::new(&encode(&t_i)) and, when
+ * masks_engines is not NULL, masks_engines[i] = MasksEngine::new(&t_i.mask), with one copy and one synchronisation. */
+int iris_engines_new_from_templates(int device, const uint64_t *templates, uint32_t num_queries,
+                                    iris_distance_engine **distance_engines, iris_masks_engine **masks_engines);
 /* encode(&Template) -> EncodedBits (src/lib.rs:16-26), computed on the device; out host or device. */
 int iris_encode(int device, const uint64_t pattern[IRIS_LIMBS], const uint64_t mask[IRIS_LIMBS],
                 uint16_t out[IRIS_BITS]);

@@ -27,6 +27,7 @@ from .api import (  # noqa: F401
     distances_batch,
     dot_bool,
     encode,
+    engines_from_templates,
     dot_u16,
     launch_count,
     lib,

@@ -69,6 +69,7 @@ def lib():
         "iris_distance_engine_new": [i32, vp, pp],
         "iris_distance_engine_free": [vp],
         "iris_distance_engine_new_from_template": [i32, vp, vp, pp],
+        "iris_engines_new_from_templates": [i32, vp, u32, vp, vp],
         "iris_encode": [i32, vp, vp, vp],
         "iris_distance_engine_batch_process": [vp, vp, u64, vp, u64],
         "iris_distance_engine_batch_process_resident": [vp, vp, u64, vp, u64, u64],
@@ -326,9 +327,12 @@ class DistanceEngine:
 class MasksEngine:
     """MasksEngine (src/lib.rs:55-79)."""
 
-    def __init__(self, query_mask, device: int = 0):
+    def __init__(self, query_mask, device: int = 0, _handle=None):
         self._h = ctypes.c_void_p()
         self.device = device
+        if _handle is not None:
+            self._h = _handle
+            return
         _check(lib().iris_masks_engine_new(device, _ptr(query_mask, np.uint64, LIMBS, "query_mask"), ctypes.byref(self._h)))
 
     def close(self) -> None:
@@ -354,6 +358,20 @@ class MasksEngine:
                 raise ValueError("db must be [n][200] u64")
             _check(lib().iris_masks_engine_batch_process(
                 self._h, _ptr(out, np.uint16, 0, "out"), _out_len(out), _ptr(db, np.uint64, 0, "db"), n))
+
+
+def engines_from_templates(templates, device: int = 0, masks: bool = True):
+    """Q wire Templates ([Q][400] u64 = {pattern[200], mask[200]} each, src/template.rs:26-29) -> (list of
+    DistanceEngine, list of MasksEngine) prepared in one batch (one copy, three launches, one synchronisation)."""
+    q = _numel(templates) // (2 * LIMBS)
+    if q * 2 * LIMBS != _numel(templates):
+        raise ValueError("templates must be [Q][400] u64")
+    de = (ctypes.c_void_p * q)()
+    me = (ctypes.c_void_p * q)() if masks else None
+    _check(lib().iris_engines_new_from_templates(device, _ptr(templates, np.uint64, q * 2 * LIMBS, "templates"), q, de, me))
+    des = [DistanceEngine(None, device, _handle=ctypes.c_void_p(h)) for h in de]
+    mes = [MasksEngine(None, device, _handle=ctypes.c_void_p(h)) for h in me] if masks else []
+    return des, mes
 
 
 def match(distance_engine: Optional[DistanceEngine], masks_engine: Optional[MasksEngine], db: Database,

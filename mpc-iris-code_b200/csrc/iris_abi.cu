@@ -578,6 +578,77 @@ extern "C" int iris_distance_engine_new_from_template(int device, const uint64_t
     return IRIS_OK;
 }
 
+// Q engines of each kind from Q wire Templates in one go: one H2D copy (3 200 B per query), three launches, one
+// synchronisation -- instead of 2Q copies, 3Q launches and 3Q synchronisations.
+extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templates, uint32_t num_queries,
+                                               iris_distance_engine** distance_engines, iris_masks_engine** masks_engines) {
+    if (!templates || !distance_engines) return fail(IRIS_ERR_INVALID, "NULL argument");
+    for (uint32_t i = 0; i < num_queries; ++i) {
+        distance_engines[i] = nullptr;
+        if (masks_engines) masks_engines[i] = nullptr;
+    }
+    if (num_queries == 0) return IRIS_OK;
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    uint8_t* d_t = nullptr;
+    CK(cudaMalloc(&d_t, (size_t)num_queries * 2 * IRIS_MASK_BYTES));
+    auto body = [&]() -> int {
+        CK(cudaMemcpyAsync(d_t, templates, (size_t)num_queries * 2 * IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+        for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxPrepBatch) {
+            const uint32_t nq = std::min<uint32_t>(kMaxPrepBatch, num_queries - q0);
+            PrepBatchParams p{};
+            p.templates = d_t + (size_t)q0 * 2 * IRIS_MASK_BYTES;
+            p.n = nq;
+            for (uint32_t i = 0; i < nq; ++i) {
+                iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
+                if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+                distance_engines[q0 + i] = e;
+                e->device = device;
+                e->fits_s8 = true;                           // encode() only yields 0, 1, 0xFFFF
+                int r = pooled_alloc(g_pool.q16, device, IRIS_BITS * sizeof(uint16_t), reinterpret_cast<void**>(&e->d_query));
+                if (r) return r;
+                r = pooled_alloc(g_pool.qd, device, kQdBytes, reinterpret_cast<void**>(&e->d_qd));
+                if (r) return r;
+                p.query[i] = e->d_query;
+                p.qd[i] = e->d_qd;
+                if (masks_engines) {
+                    iris_masks_engine* m = new (std::nothrow) iris_masks_engine();
+                    if (!m) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+                    masks_engines[q0 + i] = m;
+                    m->device = device;
+                    r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&m->d_qmask));
+                    if (r) return r;
+                    r = pooled_alloc(g_pool.qm, device, kQmBytes, reinterpret_cast<void**>(&m->d_qm));
+                    if (r) return r;
+                    CK(cudaMemcpyAsync(m->d_qmask, p.templates + (size_t)i * 2 * IRIS_MASK_BYTES + IRIS_MASK_BYTES, IRIS_MASK_BYTES,
+                                       cudaMemcpyDeviceToDevice, cudaStreamPerThread));
+                    p.qm[i] = m->d_qm;
+                }
+            }
+            CK(launch_prep_batch(p, cudaStreamPerThread));
+        }
+        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        return IRIS_OK;
+    };
+    rc = body();
+    cudaStreamSynchronize(cudaStreamPerThread);
+    cudaFree(d_t);
+    if (rc) {
+        std::string keep = g_last_error;
+        for (uint32_t i = 0; i < num_queries; ++i) {
+            iris_distance_engine_free(distance_engines[i]);
+            distance_engines[i] = nullptr;
+            if (masks_engines) {
+                iris_masks_engine_free(masks_engines[i]);
+                masks_engines[i] = nullptr;
+            }
+        }
+        g_last_error = keep;
+    }
+    return rc;
+}
+
 extern "C" int iris_distance_engine_free(iris_distance_engine* e) {
     if (!e) return IRIS_OK;
     DeviceGuard g(e->device);

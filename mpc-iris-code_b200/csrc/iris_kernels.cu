@@ -403,6 +403,73 @@ cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint1
     return cudaGetLastError();
 }
 
+// Batched query preparation: Q wire Templates (3 200 B each: pattern, mask) -> Q encoded queries, Q distance
+// operand images and Q mask operand images in three launches.
+__global__ void encode_batch_kernel(const PrepBatchParams p) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = blockIdx.y;
+    if (k >= IRIS_BITS) return;
+    const uint8_t* t = p.templates + (size_t)q * 2 * IRIS_MASK_BYTES;
+    const uint32_t m = (t[IRIS_MASK_BYTES + (k >> 3)] >> (k & 7)) & 1u;
+    const uint32_t v = (t[k >> 3] >> (k & 7)) & m;
+    p.query[q][k] = (uint16_t)(m - v - v);
+}
+__global__ void prep_distance_batch_kernel(const PrepBatchParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (c, j, ch)
+    const uint32_t qi = blockIdx.y;
+    if (idx >= kChunks * 32 * 8) return;
+    const uint16_t* __restrict__ q = p.query[qi];
+    const int ch = idx & 7, j = (idx >> 3) & 31, c = idx >> 8;
+    uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    if (j < IRIS_ROTATIONS) {
+        const int rot = j - 15;
+        for (int b = 0; b < 16; ++b) {
+            const int k = c * kChunkK + ch * 16 + b;
+            const int row = k / IRIS_COLS, col = k % IRIS_COLS;
+            const uint32_t v = q[row * IRIS_COLS + (col - rot + IRIS_COLS) % IRIS_COLS];
+            lo[b >> 2] |= (v & 0xFFu) << (8 * (b & 3));
+            hi[b >> 2] |= (v >> 8) << (8 * (b & 3));
+        }
+    }
+    const size_t off = (size_t)c * kQdChunkBytes + j * 128 + ((ch ^ (j & 7)) << 4);
+    *reinterpret_cast<uint4*>(p.qd[qi] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(p.qd[qi] + off + kQTileBytes) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+__global__ void prep_mask_batch_kernel(const PrepBatchParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (c, j, ch)
+    const uint32_t qi = blockIdx.y;
+    if (idx >= kChunks * 32 * 8) return;
+    const uint8_t* __restrict__ qmask = p.templates + (size_t)qi * 2 * IRIS_MASK_BYTES + IRIS_MASK_BYTES;
+    const int ch = idx & 7, j = (idx >> 3) & 31, c = idx >> 8;
+    uint32_t out[4] = {0, 0, 0, 0};
+    if (j < IRIS_ROTATIONS) {
+        const int rot = j - 15;
+        for (int b = 0; b < 16; ++b) {
+            const int e = ch * 16 + b;
+            const int w = e >> 5, t = (e >> 2) & 7, m = e & 3;
+            const int s = c * kChunkK + 32 * w + 8 * m + t;
+            const int row = s / IRIS_COLS, col = s % IRIS_COLS;
+            const int src = row * IRIS_COLS + (col - rot + IRIS_COLS) % IRIS_COLS;
+            const uint32_t bit = (qmask[src >> 3] >> (src & 7)) & 1u;
+            out[b >> 2] |= (bit << (7 - t)) << (8 * (b & 3));
+        }
+    }
+    const size_t off = (size_t)c * kQmChunkBytes + j * 128 + ((ch ^ (j & 7)) << 4);
+    *reinterpret_cast<uint4*>(p.qm[qi] + off) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+cudaError_t launch_prep_batch(const PrepBatchParams& p, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    encode_batch_kernel<<<dim3((IRIS_BITS + 255) / 256, p.n), 256, 0, stream>>>(p);
+    count_launch();
+    prep_distance_batch_kernel<<<dim3((kChunks * 32 * 8 + 255) / 256, p.n), 256, 0, stream>>>(p);
+    count_launch();
+    if (p.qm[0]) {
+        prep_mask_batch_kernel<<<dim3((kChunks * 32 * 8 + 255) / 256, p.n), 256, 0, stream>>>(p);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_prep_distance_query(const uint16_t* d_query, uint8_t* d_qd, cudaStream_t stream) {
     prep_distance_query_kernel<<<(kChunks * 32 * 8 + 255) / 256, 256, 0, stream>>>(d_query, d_qd);
     count_launch();

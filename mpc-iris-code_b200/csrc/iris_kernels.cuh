@@ -31,6 +31,16 @@ cudaError_t launch_mask_scan(const ScanParams& p, int num_sms, cudaStream_t stre
 // Query preparation (K3): reference DistanceEngine::new / MasksEngine::new (src/lib.rs:33-40, 60-67).
 cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint16_t* d_out, cudaStream_t stream);
 cudaError_t launch_prep_distance_query(const uint16_t* d_query, uint8_t* d_qd, cudaStream_t stream);
+// Batched preparation from wire Templates ({pattern, mask}, 3 200 B each, device): encode + both operand images.
+constexpr int kMaxPrepBatch = 64;
+struct PrepBatchParams {
+    const uint8_t* templates;            // [n][3200] device
+    uint16_t* query[kMaxPrepBatch];      // encoded query of each engine
+    uint8_t* qd[kMaxPrepBatch];          // distance operand images
+    uint8_t* qm[kMaxPrepBatch];          // mask operand images (all null: skip)
+    uint32_t n;
+};
+cudaError_t launch_prep_batch(const PrepBatchParams& p, cudaStream_t stream);
 cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, cudaStream_t stream);
 
 // Loader: reference-layout rows (device staging) -> tiled HBM image, starting at global row row0.
