@@ -23,3 +23,7 @@ cap batch_distances_u8 'batch_distances_kernel' 4
 cap batch_denominators 'batch_denominators_kernel' 1
 cap combine_decode 'combine_decode_kernel' 0
 du -sh $OUT
+# launch list of the bench command itself (the timed region is the scan_kernel launches, one per step)
+B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras"
+timeout 300 $B > $OUT/bench_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bench.csv $B > $OUT/launches_bench.log 2>&1
+echo "bench launch list rc $?"
