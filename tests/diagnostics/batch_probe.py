@@ -1,6 +1,6 @@
 """Diagnostic + timing run of the batched (dense GEMM) distances path on a B200 box.
 
-    python tools/batch_probe.py [n_rows_timing] [n_queries_timing]
+    python tests/diagnostics/batch_probe.py [n_rows_timing] [n_queries_timing]
 """
 import os
 import sys
@@ -9,7 +9,7 @@ import traceback
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import mpc_iris_code_b200 as iris  # noqa: E402
 import oracle as O  # noqa: E402

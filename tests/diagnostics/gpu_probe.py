@@ -1,7 +1,7 @@
 """Diagnostic run for a B200 box: exercises every kernel at small size against the oracle and
 prints what differs and how (layout, generator, per-product raw accumulators, final outputs).
 
-    python tools/gpu_probe.py [n_rows]
+    python tests/diagnostics/gpu_probe.py [n_rows]
 """
 import os
 import sys
@@ -9,7 +9,7 @@ import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import mpc_iris_code_b200 as iris  # noqa: E402
 import oracle as O  # noqa: E402

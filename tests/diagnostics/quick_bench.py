@@ -1,6 +1,6 @@
 """Kernel-only timing of the three scan modes on a synthetic resident database.
 
-    python tools/quick_bench.py [n_rows] [iters]
+    python tests/diagnostics/quick_bench.py [n_rows] [iters]
 """
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import mpc_iris_code_b200 as iris  # noqa: E402
 import oracle as O  # noqa: E402

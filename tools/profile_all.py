@@ -11,7 +11,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import mpc_iris_code_b200 as iris  # noqa: E402
-import oracle as O  # noqa: E402
 
 
 def main():
@@ -19,9 +18,10 @@ def main():
     brows = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000
     db = iris.Database(rows)
     db.generate(0x1715C0DE, 0, rows)
-    qm = O.gen_mask_rows(5, 1, 1)[0]
-    q = O.encode(O.gen_mask_rows(5, 0, 1)[0], qm)
-    de, me = iris.DistanceEngine(q), iris.MasksEngine(qm)
+    rng = np.random.default_rng(5)
+    tmpl = rng.integers(0, 2**64, size=(1 + 64, 400), dtype=np.uint64)      # wire Templates {pattern, mask}
+    qm = tmpl[0, 200:].copy()
+    de, me = iris.DistanceEngine.from_template(tmpl[0, :200].copy(), qm), iris.MasksEngine(qm)
     dist = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
     den = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
     for _ in range(3):
@@ -33,9 +33,8 @@ def main():
     db.synchronize()
     nq = 64
     big = torch.empty((nq, brows, 31), dtype=torch.int16, device="cuda")
-    tern = [iris.DistanceEngine(O.encode(O.gen_mask_rows(100 + i, 0, 1)[0], O.gen_mask_rows(100 + i, 1, 1)[0])) for i in range(nq)]
-    unif = [iris.DistanceEngine(O.gen_share_rows(200 + i, 0, 1)[0]) for i in range(nq)]
-    mes = [iris.MasksEngine(O.gen_mask_rows(100 + i, 1, 1)[0]) for i in range(nq)]
+    tern, mes = iris.engines_from_templates(tmpl[1:])
+    unif = [iris.DistanceEngine(x) for x in rng.integers(0, 2**16, size=(nq, 12800), dtype=np.uint16)]
     for _ in range(3):
         iris.distances_batch(tern, db, 0, brows, big)      # batch_distances_kernel<1>
     for _ in range(3):
