@@ -429,8 +429,16 @@ static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t
     if (rc) return rc;
     const uint64_t aligned0 = row_begin / kTileRows * kTileRows;
     uint64_t cb = row_begin;
+    // Chunks of 8 tiles per SM, halving towards the end (never below one tile per SM): the last device->host copy is
+    // the only one that is not hidden behind a scan, so it should be short.
+    const uint64_t wave_rows = (uint64_t)db->num_sms * kTileRows;
+    uint64_t next_edge = aligned0;
     for (uint64_t i = 0; cb < row_end; ++i) {
-        const uint64_t ce = std::min(row_end, aligned0 + (i + 1) * chunk_rows);
+        const uint64_t remaining = row_end > next_edge ? row_end - next_edge : 0;
+        uint64_t step = chunk_rows;
+        if (remaining < 2 * chunk_rows) step = std::max(wave_rows, remaining / 2 / wave_rows * wave_rows);
+        next_edge += step;
+        const uint64_t ce = std::min(row_end, next_edge);
         const int b = (int)(i & 1);
         if (i >= 2) CK(cudaStreamWaitEvent(db->stream, db->ev_copy[b], 0));
         p.dist_out = qd ? (dist_dev ? dist_out + (cb - row_begin) * IRIS_ROTATIONS : db->d_res[b][0]) : nullptr;
