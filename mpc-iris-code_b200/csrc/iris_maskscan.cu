@@ -16,7 +16,8 @@
 //
 // Per stage: 256 mask bits of 2 x 128 rows = 2 x 4 KiB of packed database (contiguous per tile) + 8 KiB of operand.
 //   producer (warp 4)     : 3 bulk copies into a 12-deep smem ring
-//   expanders (warps 7-14): LDS packed bits -> 64 LOP3 -> 2 x tcgen05.st.32x32b.x32 into a 3-deep TMEM ring
+//   expanders (warps 7-22): LDS packed bits -> 64 LOP3 -> 2 x tcgen05.st.32x32b.x32 into a 3-deep TMEM ring;
+//                           two sets of 8 warps alternate stages to overlap their per-stage latency chain
 //   issuers (warps 5, 6)  : 8 x tcgen05.mma kind::i8 (A = TMEM, B = smem) per stage, one warp per tile
 //   epilogue (warps 0-3)  : tcgen05.ld, >> 7, 62-byte rows; accumulators double-buffered
 #include <cuda_runtime.h>
@@ -40,8 +41,11 @@ constexpr int kMsARing = 3;                                       // TMEM A slot
 constexpr int kMsOutStageBytes = 8192;
 constexpr int kMsSmemBytes = 1024 + kMsStages * kMsStageBytes + kMsOutStageBytes + 512;
 constexpr int kMsIssuerWarp0 = 5;                                 // warps 5, 6
-constexpr int kMsExpWarp0 = 7;                                    // warps 7..14: 4 per tile, one per TMEM lane quadrant
-constexpr int kMsThreads = (kMsExpWarp0 + 4 * kMsTiles) * 32;     // 480
+constexpr int kMsExpWarp0 = 7;                                    // expander warps: [set][tile][TMEM lane quadrant]
+constexpr int kMsExpSets = 2;                                     // sets alternate stages: an expander's per-stage chain
+                                                                  // (LDS -> LOP -> tcgen05.st -> wait::st -> arrive) is
+                                                                  // ~600 cycles of latency, so two sets overlap it
+constexpr int kMsThreads = (kMsExpWarp0 + kMsExpSets * 4 * kMsTiles) * 32;     // 736
 constexpr uint32_t kMsAccCols = 2 * kMsTiles * 32;                // [buffer][tile] x 32 columns
 constexpr uint32_t kMsASlotCols = kMsTiles * kMsSub * 32;         // 128
 constexpr uint32_t kMsTmemCols = 512;
@@ -211,14 +215,20 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
         }
     } else if (warp >= kMsExpWarp0) {
         // ------------------------------------------------------------------ expanders: packed bits -> TMEM A operand
-        const int t = (warp - kMsExpWarp0) >> 2;          // row tile of this warp
+        const int set = (warp - kMsExpWarp0) / (4 * kMsTiles);       // which stages (g % kMsExpSets) this warp expands
+        const int t = ((warp - kMsExpWarp0) >> 2) % kMsTiles;       // row tile of this warp
         const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         int stage = 0, ar = 0;
-        uint32_t phase = 0, aphase = 0;
+        uint32_t phase = 0, aphase = 0, g = 0;
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
-            for (int c = 0; c < kMsStagesPerTile; ++c) {
+            for (int c = 0; c < kMsStagesPerTile; ++c, ++g) {
+                if ((int)(g % kMsExpSets) != set) {       // the other set's stage: only keep the ring state in step
+                    if (++stage == kMsStages) { stage = 0; phase ^= 1u; }
+                    if (++ar == kMsARing) { ar = 0; aphase ^= 1u; }
+                    continue;
+                }
                 ptx::mbar_wait(full_bar(stage), phase, p.error, kWsExpFull);
                 ptx::mbar_wait(aempty_bar(ar, t), aphase ^ 1u, p.error, kWsExpA);
                 ptx::tc_fence_after();
