@@ -8,11 +8,11 @@
 // (scan_kernel<false,true>) far below the HBM roofline.
 //
 // A CTA owns TWO consecutive 128-row tiles that share every query chunk (halves the operand traffic over the
-// L2->SM fabric), and each tile has its OWN issuing warp and accumulators.  Measured: ~690 SM cycles per 8 KiB of
-// packed database regardless of expander count, issuer count, ring depths or operand traffic (A/B experiments,
-// DESIGN.md 5.3) -- i.e. ~95 B/clk of EXPANDED operand: with N = 32 every A byte feeds only 32 MACs, so the UMMA is
-// bound by its A-operand fetch (4 KiB per 16 cycles of math), not by HBM.  More columns per A byte (the batched
-// kernel) or 4-bit operands are the only ways past ~0.5 of the HBM roofline for a single query.
+// L2->SM fabric), and each tile has its OWN issuing warp and accumulators.  An expander warp's per-stage chain
+// (LDS -> LOP -> tcgen05.st -> wait::st -> arrive) is ~600 cycles of LATENCY, so two sets of expander warps take
+// alternate stages (splitting one stage over more warps does not help; measured).  With that the
+// kernel runs at the L2->SM limit (8 KiB of query operand per 8 KiB of database): 0.37 ms per 1 M rows, 0.70 of the
+// HBM roofline.
 //
 // Per stage: 256 mask bits of 2 x 128 rows = 2 x 4 KiB of packed database (contiguous per tile) + 8 KiB of operand.
 //   producer (warp 4)     : 3 bulk copies into a 12-deep smem ring
