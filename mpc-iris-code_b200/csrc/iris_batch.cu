@@ -21,6 +21,7 @@
 //   tempty    leader  : count 8 -- one arrive per epilogue warp of both CTAs once TMEM has been drained
 #include <cuda_runtime.h>
 
+#include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
 #include "iris_ptx.cuh"
 
@@ -47,21 +48,6 @@ struct BatchCfg {
 
 enum BatchWatchdog { kWbProducer = 201, kWbFull = 202, kWbReady = 203, kWbTmemEmpty = 204, kWbEpilogue = 205 };
 
-__device__ __forceinline__ void copy_out_rows(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
-    if (b1 <= b0) return;
-    int body0 = (b0 + 15) & ~15, body1 = b1 & ~15;
-    if (body0 > body1) {
-        for (int b = b0 + 2 * tid; b < b1; b += 2 * 128)
-            *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-        return;
-    }
-    for (int b = b0 + 2 * tid; b < body0; b += 2 * 128)
-        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-    for (int b = body0 + 16 * tid; b < body1; b += 16 * 128)
-        *reinterpret_cast<uint4*>(gbase + b) = *reinterpret_cast<const uint4*>(stage + b);
-    for (int b = body1 + 2 * tid; b < b1; b += 2 * 128)
-        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-}
 
 template <bool SIGNED_Q>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)

@@ -1,0 +1,27 @@
+// Shared epilogue helper of the scan / batched kernels: result rows are 62 bytes (31 x u16, the reference's wire
+// format, src/main.rs:429-431), so a tile's rows are staged in shared memory with the same 16-byte phase as their
+// destination and then stored with 128-bit accesses.
+#pragma once
+#include <stdint.h>
+
+namespace iris {
+
+// Copies bytes [b0,b1) (offsets inside `stage`, both even) to gbase + offset, where gbase is 16-byte aligned and
+// congruent with `stage`: 16-byte body, 2-byte head / tail.  Executed by the 128 epilogue threads (tid 0..127).
+__device__ __forceinline__ void copy_out_rows(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
+    if (b1 <= b0) return;
+    int body0 = (b0 + 15) & ~15, body1 = b1 & ~15;
+    if (body0 > body1) {  // shorter than one aligned vector
+        for (int b = b0 + 2 * tid; b < b1; b += 2 * 128)
+            *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
+        return;
+    }
+    for (int b = b0 + 2 * tid; b < body0; b += 2 * 128)
+        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
+    for (int b = body0 + 16 * tid; b < body1; b += 16 * 128)
+        *reinterpret_cast<uint4*>(gbase + b) = *reinterpret_cast<const uint4*>(stage + b);
+    for (int b = body1 + 2 * tid; b < b1; b += 2 * 128)
+        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
+}
+
+}  // namespace iris

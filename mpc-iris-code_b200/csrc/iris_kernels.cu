@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdlib>
 
+#include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
 #include "iris_ptx.cuh"
 
@@ -52,7 +53,7 @@ struct ScanCfg {
     static_assert(kSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
 };
 
-constexpr int kEpilogueWarps = 4;     // warps 0..3  (TMEM lane quadrant = warp index)
+// warps 0..3: epilogue (TMEM lane quadrant = warp index)
 constexpr int kProducerWarp = 4;
 constexpr int kMmaWarp = 5;
 constexpr int kExpanderWarp0 = 6;     // warps 6..9
@@ -62,23 +63,6 @@ constexpr uint32_t kTmemCols = 256;   // 2 accumulator buffers x 128 columns
 
 enum WatchdogCode { kWdProducer = 101, kWdMmaFull = 102, kWdMmaExp = 103, kWdMmaTmem = 104, kWdExpander = 105, kWdEpilogue = 106 };
 
-// Copies [b0,b1) (byte offsets inside `stage`, both even) to gbase+offset, where gbase is 16-byte
-// aligned and congruent with `stage`: 16-byte body, 2-byte head/tail.  Executed by 128 threads.
-__device__ __forceinline__ void copy_out(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
-    if (b1 <= b0) return;
-    int body0 = (b0 + 15) & ~15, body1 = b1 & ~15;
-    if (body0 > body1) {  // shorter than one aligned vector
-        for (int b = b0 + 2 * tid; b < b1; b += 2 * 128)
-            *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-        return;
-    }
-    for (int b = b0 + 2 * tid; b < body0; b += 2 * 128)
-        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-    for (int b = body0 + 16 * tid; b < body1; b += 16 * 128)
-        *reinterpret_cast<uint4*>(gbase + b) = *reinterpret_cast<const uint4*>(stage + b);
-    for (int b = body1 + 2 * tid; b < b1; b += 2 * 128)
-        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-}
 
 template <bool S, bool M, bool SQ>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams p) {
@@ -285,12 +269,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
             if (S) {
                 const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(p.dist_out) + tile_off) & 15);
                 uint8_t* g = reinterpret_cast<uint8_t*>(p.dist_out) + tile_off - shift;
-                copy_out(out_stage_ptr, g, (int)shift + r0 * kOutRowBytes, (int)shift + r1 * kOutRowBytes, row);
+                copy_out_rows(out_stage_ptr, g, (int)shift + r0 * kOutRowBytes, (int)shift + r1 * kOutRowBytes, row);
             }
             if (M) {
                 const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(p.den_out) + tile_off) & 15);
                 uint8_t* g = reinterpret_cast<uint8_t*>(p.den_out) + tile_off - shift;
-                copy_out(out_stage_ptr + Cfg::kOutStageBytes, g, (int)shift + r0 * kOutRowBytes,
+                copy_out_rows(out_stage_ptr + Cfg::kOutStageBytes, g, (int)shift + r0 * kOutRowBytes,
                          (int)shift + r1 * kOutRowBytes, row);
             }
             ptx::named_bar_sync(1, 128);

@@ -22,6 +22,7 @@
 //   epilogue (warps 0-3)  : tcgen05.ld, >> 7, 62-byte rows; accumulators double-buffered
 #include <cuda_runtime.h>
 
+#include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
 #include "iris_ptx.cuh"
 
@@ -84,21 +85,6 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
 
-__device__ __forceinline__ void ms_copy_out(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
-    if (b1 <= b0) return;
-    int body0 = (b0 + 15) & ~15, body1 = b1 & ~15;
-    if (body0 > body1) {
-        for (int b = b0 + 2 * tid; b < b1; b += 2 * 128)
-            *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-        return;
-    }
-    for (int b = b0 + 2 * tid; b < body0; b += 2 * 128)
-        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-    for (int b = body0 + 16 * tid; b < body1; b += 16 * 128)
-        *reinterpret_cast<uint4*>(gbase + b) = *reinterpret_cast<const uint4*>(stage + b);
-    for (int b = body1 + 2 * tid; b < b1; b += 2 * 128)
-        *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
-}
 
 // p.tile_begin / p.tile_end are in units of 128-row tiles; this kernel walks PAIRS of tiles
 // [tile_begin/2, ceil(tile_end/2)) -- the shard's capacity is a whole number of pairs and zero filled.
@@ -284,7 +270,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
                 for (int j = 0; j < IRIS_ROTATIONS; ++j) *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)(a[j] >> 7);
                 ptx::named_bar_sync(1, 128);
                 if (r1 > r0)
-                    ms_copy_out(out_stage_ptr, reinterpret_cast<uint8_t*>(p.den_out) + tile_off - shift,
+                    copy_out_rows(out_stage_ptr, reinterpret_cast<uint8_t*>(p.den_out) + tile_off - shift,
                                 (int)shift + r0 * kOutRowBytes, (int)shift + r1 * kOutRowBytes, row);
                 ptx::named_bar_sync(1, 128);
             }
