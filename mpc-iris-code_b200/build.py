@@ -67,18 +67,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 BIN_DIR = os.path.join(HERE, "bin")
 PARTICIPANT_PATH = os.path.join(BIN_DIR, "iris_participant")
+COORDINATOR_PATH = os.path.join(BIN_DIR, "iris_coordinator")
+
+
+def _build_front_end(source: str, target: str) -> str:
+    os.makedirs(BIN_DIR, exist_ok=True)
+    tmp = target + f".tmp{os.getpid()}"
+    subprocess.check_call([
+        "g++", "-O2", "-std=c++17", "-Wall", "-o", tmp, os.path.join(CSRC, source),
+        "-L" + LIB_DIR, "-liris_b200", "-Wl,-rpath,$ORIGIN/../lib",
+    ])
+    os.replace(tmp, target)
+    return target
 
 
 def build_participant() -> str:
-    """The wire-protocol front-end (reference `participant`, src/main.rs:384-452) over the C ABI: plain g++."""
-    os.makedirs(BIN_DIR, exist_ok=True)
-    tmp = PARTICIPANT_PATH + f".tmp{os.getpid()}"
-    subprocess.check_call([
-        "g++", "-O2", "-std=c++17", "-o", tmp, os.path.join(CSRC, "participant_main.cpp"),
-        "-L" + LIB_DIR, "-liris_b200", "-Wl,-rpath,$ORIGIN/../lib",
-    ])
-    os.replace(tmp, PARTICIPANT_PATH)
-    return PARTICIPANT_PATH
+    """The wire-protocol front-ends over the C ABI, plain g++: reference `participant` (src/main.rs:384-452) and
+    the query loop of `coordinator` (src/main.rs:453-640).  Returns the participant's path."""
+    _build_front_end("coordinator_main.cpp", COORDINATOR_PATH)
+    return _build_front_end("participant_main.cpp", PARTICIPANT_PATH)
 
 
 if __name__ == "__main__":

@@ -10,9 +10,13 @@
 // A CTA owns TWO consecutive 128-row tiles that share every query chunk (halves the operand traffic over the
 // L2->SM fabric), and each tile has its OWN issuing warp and accumulators.  An expander warp's per-stage chain
 // (LDS -> LOP -> tcgen05.st -> wait::st -> arrive) is ~600 cycles of LATENCY, so two sets of expander warps take
-// alternate stages (splitting one stage over more warps does not help; measured).  With that the
-// kernel runs at the L2->SM limit (8 KiB of query operand per 8 KiB of database): 0.37 ms per 1 M rows, 0.70 of the
-// HBM roofline.
+// alternate stages (splitting one stage over more warps does not help; measured).
+//
+// What bounds it is the tensor-core side, not HBM: with the expanders switched off (timing experiment) the UMMAs
+// alone take 0.354 ms per 1 M rows -- one M=128, N=32, K=32 kind::i8 instruction per ~31 cycles per SM although
+// its MACs need 16, which matches a 4 KiB A operand entering at 128 B/clk (12.8 GB of expanded operand per 1 M
+// rows).  The complete kernel takes 0.363-0.373 ms alone (0.70 of the HBM roofline).  Multicasting the query
+// operand across a cluster of two halves the L2 reads and changes nothing; details in DESIGN.md 5.3.
 //
 // Per stage: 256 mask bits of 2 x 128 rows = 2 x 4 KiB of packed database (contiguous per tile) + 8 KiB of operand.
 //   producer (warp 4)     : 3 bulk copies into a 12-deep smem ring
@@ -43,7 +47,7 @@ constexpr int kMsOutStageBytes = 8192;
 constexpr int kMsSmemBytes = 1024 + kMsStages * kMsStageBytes + kMsOutStageBytes + 512;
 constexpr int kMsIssuerWarp0 = 5;                                 // warps 5, 6
 constexpr int kMsExpWarp0 = 7;                                    // expander warps: [set][tile][TMEM lane quadrant]
-constexpr int kMsExpSets = 2;                                     // sets alternate stages: an expander's per-stage chain
+constexpr int kMsExpSets = 2;                                    // sets alternate stages: an expander's per-stage chain
                                                                   // (LDS -> LOP -> tcgen05.st -> wait::st -> arrive) is
                                                                   // ~600 cycles of latency, so two sets overlap it
 constexpr int kMsThreads = (kMsExpWarp0 + kMsExpSets * 4 * kMsTiles) * 32;     // 736

@@ -67,6 +67,29 @@ def test_no_cpu_fallback_without_a_gpu():
         assert ei.value.code == -2
 
 
+def test_front_ends_build_and_fail_loudly_without_a_gpu(tmp_path):
+    """iris_participant / iris_coordinator (reference src/main.rs:384-640) link against the C ABI only; without a
+    device they must exit non-zero with the library's error, not serve anything."""
+    import subprocess
+
+    import torch
+
+    from mpc_iris_code_b200 import build
+
+    build.build_participant()
+    assert subprocess.run([build.PARTICIPANT_PATH]).returncode == 2          # usage
+    assert subprocess.run([build.COORDINATOR_PATH]).returncode == 2
+    if torch.cuda.is_available():
+        return
+    np.zeros((3, 200), np.uint64).tofile(tmp_path / "mpc.masks")
+    r = subprocess.run([build.COORDINATOR_PATH, "--masks", str(tmp_path / "mpc.masks"), "127.0.0.1:9"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "iris_db_create" in r.stderr
+    np.zeros((3, 12800), np.uint16).tofile(tmp_path / "mpc.share-0")
+    r = subprocess.run([build.PARTICIPANT_PATH, "--input", str(tmp_path / "mpc.share-0")], capture_output=True, text=True)
+    assert r.returncode == 1 and "iris_db_create" in r.stderr
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "mpc-iris-code_b200")
     for dirpath, _, files in os.walk(pkg):
