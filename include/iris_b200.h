@@ -94,6 +94,16 @@ int iris_db_read_masks(iris_db *db, uint64_t row_begin, uint64_t n, uint64_t *ou
 int iris_db_set_stream(iris_db *db, void *cuda_stream);
 int iris_db_synchronize(iris_db *db);
 
+/* ---- page-locked host buffers for result slices.  The reference allocates a fresh Vec per chunk
+ * (src/main.rs:429, 514); any host memory works here too, but device->host copies into page-locked
+ * memory run at the full PCIe rate and overlap the scan. ---- */
+int iris_host_alloc(uint64_t bytes, void **out);
+int iris_host_free(void *ptr);
+/* Device buffers for results that stay in HBM between calls (e.g. the coordinator's denominators, which
+ * iris_combine_min consumes), for callers that do not link the CUDA runtime themselves. */
+int iris_device_alloc(int device, uint64_t bytes, void **out);
+int iris_device_free(int device, void *ptr);
+
 /* ---- DistanceEngine (src/lib.rs:28-52) ---- */
 /* new: prepares the 31 rotations (-15..=15) of `query` as the tensor-core operand image. */
 int iris_distance_engine_new(int device, const uint16_t query[IRIS_BITS], iris_distance_engine **out);

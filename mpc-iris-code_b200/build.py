@@ -74,7 +74,7 @@ def _build_front_end(source: str, target: str) -> str:
     os.makedirs(BIN_DIR, exist_ok=True)
     tmp = target + f".tmp{os.getpid()}"
     subprocess.check_call([
-        "g++", "-O2", "-std=c++17", "-Wall", "-o", tmp, os.path.join(CSRC, source),
+        "g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", tmp, os.path.join(CSRC, source),
         "-L" + LIB_DIR, "-liris_b200", "-Wl,-rpath,$ORIGIN/../lib",
     ])
     os.replace(tmp, target)

@@ -28,6 +28,7 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <chrono>
 #include <cinttypes>
 #include <cmath>
 #include <csignal>
@@ -35,8 +36,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <limits>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/iris_b200.h"
@@ -165,8 +169,25 @@ int main(int argc, char** argv) {
     }
 
     const size_t parties = participants.size();
-    std::vector<uint16_t> denominators(count * IRIS_ROTATIONS);
-    std::vector<std::vector<uint16_t>> batches(parties, std::vector<uint16_t>(batch_rows * IRIS_ROTATIONS));
+    const size_t batch_bytes = batch_rows * kRowBytes;
+    constexpr uint64_t kRing = 3;                                         // batches buffered per participant
+    // Denominators stay in HBM; the share batches land in page-locked rings, one reader thread per participant
+    // (the reference polls all streams concurrently with try_join_all, src/main.rs:525-560).
+    uint16_t* d_denominators = nullptr;
+    if (iris_device_alloc(device, (count ? count : 1) * kRowBytes, reinterpret_cast<void**>(&d_denominators)))
+        die("iris_device_alloc");
+    struct Stream {
+        int fd = -1;
+        uint16_t* ring[kRing] = {};
+        uint64_t rows[kRing] = {};          // whole rows in each buffered batch
+        uint64_t produced = 0;              // batches read (guarded by mu)
+        bool eof = false;
+        std::thread reader;
+    };
+    std::vector<Stream> streams(parties);
+    for (Stream& s : streams)
+        for (uint16_t*& slot : s.ring)
+            if (iris_host_alloc(batch_bytes, reinterpret_cast<void**>(&slot))) die("iris_host_alloc");
     std::vector<const uint16_t*> share_ptrs(parties);
     uint64_t tmpl[2 * IRIS_LIMBS];
     for (long request = 0; request < requests; ++request) {
@@ -176,46 +197,90 @@ int main(int argc, char** argv) {
             for (uint64_t& w : tmpl) w = splitmix64(seed);               // thread_rng().gen::<Template>()
         }
 
-        std::vector<int> streams;
-        for (const std::string& address : participants) {
-            int fd = connect_to(address);
+        using clock = std::chrono::steady_clock;
+        auto ms_since = [](clock::time_point t) { return std::chrono::duration<double, std::milli>(clock::now() - t).count(); };
+        const clock::time_point t_request = clock::now();
+        double ms_wait = 0, ms_combine = 0;
+        for (size_t i = 0; i < parties; ++i) {
+            const int fd = connect_to(participants[i]);
             if (fd < 0) {
-                fprintf(stderr, "Could not connect to %s\n", address.c_str());
+                fprintf(stderr, "Could not connect to %s\n", participants[i].c_str());
                 return 1;
             }
             if (!write_all(fd, tmpl, kTemplateBytes)) {                   // stream.write_all(bytes_of(&query))
-                fprintf(stderr, "Could not send the request to %s\n", address.c_str());
+                fprintf(stderr, "Could not send the request to %s\n", participants[i].c_str());
                 return 1;
             }
-            streams.push_back(fd);
+            streams[i].fd = fd;
+            streams[i].produced = 0;
+            streams[i].eof = false;
         }
 
-        // MasksEngine::new(&query.mask) + batch_process over all the masks (src/main.rs:511-516)
+        std::mutex mu;
+        std::condition_variable cv;
+        uint64_t consumed = 0;                                            // batches combined
+        bool stop = false;
+        for (size_t i = 0; i < parties; ++i) {
+            Stream& s = streams[i];
+            s.reader = std::thread([&, i] {
+                for (uint64_t b = 0;; ++b) {
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return stop || b - consumed < kRing; });
+                        if (stop) return;
+                    }
+                    // fill the whole batch unless the stream ends first (src/main.rs:537-556)
+                    const size_t got = read_upto(s.fd, s.ring[b % kRing], batch_bytes);
+                    if (got < batch_bytes) {
+                        fprintf(stderr, "Participant %zu finished.\n", i);
+                        if (got % kRowBytes) fprintf(stderr, "Warning: received partial results from %zu.\n", i);
+                    }
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        s.rows[b % kRing] = got / kRowBytes;             // whole rows only
+                        s.produced = b + 1;
+                        s.eof = got < batch_bytes;
+                    }
+                    cv.notify_all();
+                    if (got < batch_bytes) return;
+                }
+            });
+        }
+
+        // MasksEngine::new(&query.mask) + batch_process over all the masks (src/main.rs:507-519), while the
+        // participants work
+        const double ms_connect = ms_since(t_request);
+        const clock::time_point t_den = clock::now();
         iris_masks_engine* engine = nullptr;
         if (iris_masks_engine_new(device, tmpl + IRIS_LIMBS, &engine)) die("iris_masks_engine_new");
-        if (count && iris_masks_engine_batch_process_resident(engine, denominators.data(), count, db, 0, count))
+        if (count && iris_masks_engine_batch_process_resident(engine, d_denominators, count, db, 0, count))
             die("iris_masks_engine_batch_process_resident");
+        if (iris_db_synchronize(db)) die("iris_db_synchronize");
         iris_masks_engine_free(engine);
+        const double ms_denominators = ms_since(t_den);
 
         double min_distance = std::numeric_limits<double>::infinity();
         uint64_t min_index = UINT64_MAX;                                  // usize::MAX
         uint64_t done = 0;
-        for (;;) {
+        for (uint64_t b = 0;; ++b) {
             uint64_t batch_size = count - done < batch_rows ? count - done : batch_rows;   // denominators left
-            for (size_t i = 0; i < parties; ++i) {
-                const size_t got = read_upto(streams[i], batches[i].data(), batch_rows * kRowBytes);
-                if (got < batch_rows * kRowBytes) {
-                    fprintf(stderr, "Participant %zu finished.\n", i);
-                    if (got % kRowBytes) fprintf(stderr, "Warning: received partial results from %zu.\n", i);
+            const clock::time_point t_wait = clock::now();
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                for (size_t i = 0; i < parties; ++i) {
+                    Stream& s = streams[i];
+                    cv.wait(lk, [&] { return s.produced > b || s.eof; });
+                    const uint64_t rows = s.produced > b ? s.rows[b % kRing] : 0;   // nothing after the end
+                    if (rows < batch_size) batch_size = rows;                         // shortest prefix
+                    share_ptrs[i] = s.ring[b % kRing];
                 }
-                const uint64_t rows = got / kRowBytes;                   // whole rows only
-                if (rows < batch_size) batch_size = rows;                 // shortest prefix
-                share_ptrs[i] = batches[i].data();
             }
+            ms_wait += ms_since(t_wait);
             if (batch_size == 0) break;
+            const clock::time_point t_combine = clock::now();
             double d;
             uint64_t idx;
-            if (iris_combine_min(device, share_ptrs.data(), (uint32_t)parties, denominators.data() + done * IRIS_ROTATIONS,
+            if (iris_combine_min(device, share_ptrs.data(), (uint32_t)parties, d_denominators + done * IRIS_ROTATIONS,
                                  batch_size, done, nullptr, &d, &idx))
                 die("iris_combine_min");
             if (d < min_distance) {                                       // src/main.rs:614-617
@@ -223,18 +288,38 @@ int main(int argc, char** argv) {
                 min_index = idx;
             }
             done += batch_size;
+            ms_combine += ms_since(t_combine);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                consumed = b + 1;
+            }
+            cv.notify_all();
         }
-        for (int fd : streams) close(fd);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (Stream& s : streams) {
+            shutdown(s.fd, SHUT_RDWR);                                    // unblocks a reader still inside read()
+            s.reader.join();
+            close(s.fd);
+        }
 
         if (std::isinf(min_distance))
             fprintf(stderr, "Found closest entry at %" PRIu64 " out of %" PRIu64 " at distance inf.\n", min_index, done);
         else
             fprintf(stderr, "Found closest entry at %" PRIu64 " out of %" PRIu64 " at distance %.17g.\n", min_index, done,
                     min_distance);
+        fprintf(stderr, "Timing: %.2f ms (connect + send %.2f, denominators %.2f, waiting for shares %.2f, combine %.2f)\n",
+                ms_since(t_request), ms_connect, ms_denominators, ms_wait, ms_combine);
         printf("%" PRIu64 " %" PRIu64 " %.17g\n", min_index, done, min_distance);
         fflush(stdout);
     }
     if (qf) fclose(qf);
+    for (Stream& s : streams)
+        for (uint16_t* slot : s.ring) iris_host_free(slot);
+    iris_device_free(device, d_denominators);
     iris_db_destroy(db);
     return 0;
 }

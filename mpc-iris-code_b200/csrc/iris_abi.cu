@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -145,6 +146,25 @@ static int pooled_alloc(std::vector<std::pair<int, void*>>& v, int dev, size_t b
     return IRIS_OK;
 }
 
+// Temporary device memory that lives for one ABI call: stream-ordered allocations (cudaStreamPerThread) from the
+// device's default pool, which is told to keep what it has been given.  After the first call of a kind no
+// cudaMalloc / cudaFree -- both of which synchronise the whole device -- is left on the per-query path.
+static int temp_alloc(int device, void** out, size_t bytes) {
+    static std::atomic<bool> tuned[64];
+    if (device >= 0 && device < 64 && !tuned[device].load(std::memory_order_acquire)) {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        tuned[device].store(true, std::memory_order_release);
+    }
+    CK(cudaMallocAsync(out, bytes ? bytes : 1, cudaStreamPerThread));
+    return IRIS_OK;
+}
+static void temp_free(void* p) {
+    if (p) cudaFreeAsync(p, cudaStreamPerThread);
+}
+
 // ------------------------------------------------------------------------------------ database
 extern "C" int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags, iris_db** out) {
     if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
@@ -261,6 +281,52 @@ extern "C" int iris_db_synchronize(iris_db* db) {
     CK(cudaStreamSynchronize(db->stream));
     CK(cudaStreamSynchronize(db->copy_stream));
     return check_error_flag(db);
+}
+
+static int require_device(int device);
+
+extern "C" int iris_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(IRIS_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(IRIS_ERR_NOMEM, "cannot page-lock %llu bytes of host memory", (unsigned long long)bytes);
+    }
+    return IRIS_OK;
+}
+
+extern "C" int iris_host_free(void* ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return IRIS_OK;
+}
+
+extern "C" int iris_device_alloc(int device, uint64_t bytes, void** out) {
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (cudaMalloc(out, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(IRIS_ERR_NOMEM, "cannot allocate %llu bytes on device %d", (unsigned long long)bytes, device);
+    }
+    return IRIS_OK;
+}
+
+extern "C" int iris_device_free(int device, void* ptr) {
+    if (!ptr) return IRIS_OK;
+    int rc = require_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    CK(cudaFree(ptr));
+    return IRIS_OK;
 }
 
 static int ensure_stage(iris_db* db) {
@@ -522,7 +588,8 @@ extern "C" int iris_encode(int device, const uint64_t* pattern, const uint64_t* 
     if (rc) return rc;
     DeviceGuard g(device);
     uint8_t* d = nullptr;
-    CK(cudaMalloc(&d, 2 * IRIS_MASK_BYTES + IRIS_BITS * sizeof(uint16_t)));
+    rc = temp_alloc(device, reinterpret_cast<void**>(&d), 2 * IRIS_MASK_BYTES + IRIS_BITS * sizeof(uint16_t));
+    if (rc) return rc;
     auto body = [&]() -> int {
         uint16_t* d_out = reinterpret_cast<uint16_t*>(d + 2 * IRIS_MASK_BYTES);
         CK(cudaMemcpyAsync(d, pattern, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
@@ -533,7 +600,7 @@ extern "C" int iris_encode(int device, const uint64_t* pattern, const uint64_t* 
         return IRIS_OK;
     };
     rc = body();
-    cudaFree(d);
+    temp_free(d);
     return rc;
 }
 
@@ -600,7 +667,8 @@ extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templ
     if (rc) return rc;
     DeviceGuard g(device);
     uint8_t* d_t = nullptr;
-    CK(cudaMalloc(&d_t, (size_t)num_queries * 2 * IRIS_MASK_BYTES));
+    rc = temp_alloc(device, reinterpret_cast<void**>(&d_t), (size_t)num_queries * 2 * IRIS_MASK_BYTES);
+    if (rc) return rc;
     auto body = [&]() -> int {
         CK(cudaMemcpyAsync(d_t, templates, (size_t)num_queries * 2 * IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
         for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxPrepBatch) {
@@ -640,8 +708,8 @@ extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templ
         return IRIS_OK;
     };
     rc = body();
+    temp_free(d_t);
     cudaStreamSynchronize(cudaStreamPerThread);
-    cudaFree(d_t);
     if (rc) {
         std::string keep = g_last_error;
         for (uint32_t i = 0; i < num_queries; ++i) {
@@ -992,7 +1060,7 @@ extern "C" int iris_combine_min(int device, const uint16_t* const* distance_shar
     DeviceGuard g(device);
     std::vector<void*> owned;
     auto cleanup = [&]() {
-        for (void* q : owned) cudaFree(q);
+        for (void* q : owned) temp_free(q);
     };
     auto to_device = [&](const void* src, size_t bytes, const void** out) -> int {
         if (is_device_pointer(src) || bytes == 0) {
@@ -1000,7 +1068,8 @@ extern "C" int iris_combine_min(int device, const uint16_t* const* distance_shar
             return IRIS_OK;
         }
         void* d = nullptr;
-        CK(cudaMalloc(&d, bytes));
+        int r = temp_alloc(device, &d, bytes);
+        if (r) return r;
         owned.push_back(d);
         CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
         *out = d;
@@ -1024,13 +1093,15 @@ extern "C" int iris_combine_min(int device, const uint16_t* const* distance_shar
         if (distances_out) {
             if (dist_dev) d_dist = distances_out;
             else {
-                CK(cudaMalloc(&d_dist, n * sizeof(double) + 8));
+                r = temp_alloc(device, reinterpret_cast<void**>(&d_dist), n * sizeof(double) + 8);
+                if (r) return r;
                 owned.push_back(d_dist);
             }
         }
         p.distances_out = d_dist;
         void* scratch = nullptr;
-        CK(cudaMalloc(&scratch, combine_scratch_bytes(n) + 16));
+        r = temp_alloc(device, &scratch, combine_scratch_bytes(n) + 16);
+        if (r) return r;
         owned.push_back(scratch);
         void* result = static_cast<uint8_t*>(scratch) + (combine_scratch_bytes(n) / 16) * 16;
         CK(launch_combine_min(p, scratch, result, cudaStreamPerThread));
@@ -1063,7 +1134,8 @@ extern "C" int iris_combine_min_batch(int device, const uint16_t* distances, con
     DeviceGuard g(device);
     const size_t sbytes = (combine_scratch_bytes(n) + 15) / 16 * 16;
     uint8_t* scratch = nullptr;
-    CK(cudaMalloc(&scratch, sbytes + 16 * (size_t)num_queries));
+    rc = temp_alloc(device, reinterpret_cast<void**>(&scratch), sbytes + 16 * (size_t)num_queries);
+    if (rc) return rc;
     auto body = [&]() -> int {
         for (uint32_t q = 0; q < num_queries; ++q) {
             CombineParams p{};
@@ -1084,8 +1156,8 @@ extern "C" int iris_combine_min_batch(int device, const uint16_t* distances, con
         return IRIS_OK;
     };
     rc = body();
+    temp_free(scratch);
     cudaStreamSynchronize(cudaStreamPerThread);
-    cudaFree(scratch);
     return rc;
 }
 
@@ -1139,7 +1211,8 @@ static int dot_pair(int device, const T* a, const T* b, size_t bytes, uint16_t* 
     if (rc) return rc;
     DeviceGuard g(device);
     uint8_t* d = nullptr;
-    CK(cudaMalloc(&d, 2 * bytes + 16));
+    rc = temp_alloc(device, reinterpret_cast<void**>(&d), 2 * bytes + 16);
+    if (rc) return rc;
     int result = IRIS_OK;
     auto body = [&]() -> int {
         CK(cudaMemcpyAsync(d, a, bytes, cudaMemcpyDefault, cudaStreamPerThread));
@@ -1150,7 +1223,7 @@ static int dot_pair(int device, const T* a, const T* b, size_t bytes, uint16_t* 
         return IRIS_OK;
     };
     result = body();
-    cudaFree(d);
+    temp_free(d);
     return result;
 }
 

@@ -21,6 +21,8 @@
 //   tempty    leader  : count 8 -- one arrive per epilogue warp of both CTAs once TMEM has been drained
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
 #include "iris_ptx.cuh"
@@ -234,15 +236,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
 template <bool SIGNED_Q>
 static cudaError_t launch_batch_t(const BatchParams& p, int num_sms, cudaStream_t stream) {
     using Cfg = BatchCfg<SIGNED_Q>;
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !configured[dev]) {
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(batch_distances_kernel<SIGNED_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const uint32_t num_groups = (p.num_queries + kBatchQTile - 1) / kBatchQTile;
     const uint32_t tiles = (p.pair_end - p.pair_begin) * num_groups;
@@ -471,14 +473,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMaskThreads, 1)
 
 cudaError_t launch_batch_denominators(const BatchMaskParams& p, int num_sms, cudaStream_t stream) {
     if (p.num_queries == 0 || p.num_queries > kMaxBatchQueries) return cudaErrorInvalidValue;
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !configured[dev]) {
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(batch_denominators_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskSmemBytes);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const uint32_t num_groups = (p.num_queries + kMaskQTile - 1) / kMaskQTile;
     const uint32_t tiles = (p.pair_end - p.pair_begin) * num_groups;

@@ -289,14 +289,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
 template <bool S, bool M, bool SQ>
 static cudaError_t launch_scan_t(const ScanParams& p, int num_sms, cudaStream_t stream) {
     using Cfg = ScanCfg<S, M, SQ>;
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !configured[dev]) {
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(scan_kernel<S, M, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const uint32_t tiles = p.tile_end - p.tile_begin;
     if (tiles == 0) return cudaSuccess;

@@ -26,6 +26,8 @@
 //   epilogue (warps 0-3)  : tcgen05.ld, >> 7, 62-byte rows; accumulators double-buffered
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
 #include "iris_ptx.cuh"
@@ -287,14 +289,14 @@ __global__ void __launch_bounds__(kMsThreads, 1) mask_scan_kernel(const ScanPara
 }
 
 cudaError_t launch_mask_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !configured[dev]) {
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(mask_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsSmemBytes);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     if (p.tile_end <= p.tile_begin) return cudaSuccess;
     const uint32_t pairs = (p.tile_end + kMsTiles - 1) / kMsTiles - p.tile_begin / kMsTiles;

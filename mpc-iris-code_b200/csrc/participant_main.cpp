@@ -3,10 +3,16 @@
 //
 // Protocol (raw native-endian Pod bytes, no framing; src/main.rs:418-443):
 //   request : one 3 200-byte Template {pattern: Bits, mask: Bits}           (src/template.rs:11-29)
-//   reply   : [u16;31] per database row (62 bytes, rotation -15..=15), produced in batches of
-//             20 000 rows (src/main.rs:428, 473) and streamed back; EOF terminates the reply.
+//   reply   : [u16;31] per database row (62 bytes, rotation -15..=15), streamed back; EOF terminates the
+//             reply.  The reference produces it in batches of 20 000 rows through an mpsc(4) channel
+//             (src/main.rs:423-443); the batch boundaries are not visible on the wire.
 // One request at a time, like the reference.  An unmodified reference coordinator / benchmark
 // (src/main.rs:486-504, 645-686) can connect to this process.
+//
+// Same two-stage shape as the reference: a worker thread scans batch after batch into a small ring of page-locked
+// buffers (the channel) while the main thread writes finished batches to the socket.  Measured over loopback on
+// the B200 box, 1 M rows per request (tests/diagnostics/participant_bench.py): 7.4 ms = 1.35e8 rows/s at the
+// reference's 20 000-row batch (22 ms before the two stages overlapped; the scan alone is 3.9 ms).
 //
 //   iris_participant --input mpc.share-0 [--bind 127.0.0.1:1234] [--device 0] [--batch-size 20000]
 //                    [--max-requests N] [--synthetic ROWS --seed S]
@@ -17,13 +23,17 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cerrno>
+#include <condition_variable>
 #include <csignal>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/iris_b200.h"
@@ -65,7 +75,7 @@ static bool write_all(int fd, const void* buf, size_t n) {
 int main(int argc, char** argv) {
     std::string input, bind_addr = "127.0.0.1:1234";   // reference default, src/main.rs:124
     int device = 0;
-    uint64_t batch = 20000, synthetic = 0, seed = 0x1715C0DE;
+    uint64_t batch = 20000, synthetic = 0, seed = 0x1715C0DE;   // the reference's chunk, src/main.rs:428
     long max_requests = -1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -142,7 +152,11 @@ int main(int argc, char** argv) {
     fprintf(stderr, "Listening on %s:%d\n", bind_addr.substr(0, colon).c_str(), (int)ntohs(addr.sin_port));
     fflush(stderr);
 
-    std::vector<uint16_t> out(batch * IRIS_ROTATIONS);
+    constexpr uint64_t kRing = 3;                            // batches in flight between the scan and the socket
+    uint16_t* ring[kRing];
+    for (uint16_t*& slot : ring)
+        if (iris_host_alloc(batch * IRIS_ROTATIONS * sizeof(uint16_t), reinterpret_cast<void**>(&slot))) die("iris_host_alloc");
+    const uint64_t n_batches = (rows + batch - 1) / batch;
     uint64_t tmpl[2 * IRIS_LIMBS];
     for (long served = 0; max_requests < 0 || served < max_requests; ++served) {
         int fd = accept(ls, nullptr, nullptr);
@@ -161,16 +175,65 @@ int main(int argc, char** argv) {
         fprintf(stderr, "Request received.\n");
         iris_distance_engine* engine = nullptr;
         if (iris_distance_engine_new_from_template(device, tmpl, tmpl + IRIS_LIMBS, &engine)) die("engine");
+        std::mutex mu;
+        std::condition_variable cv;
+        uint64_t produced = 0, consumed = 0;                 // batches scanned / batches written
+        bool stop = false;
+        std::string worker_error;
+        // spawn_blocking worker of src/main.rs:425-434: for chunk in patterns.chunks(..) { batch_process; send }
+        std::thread worker([&] {
+            for (uint64_t i = 0; i < n_batches; ++i) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || i - consumed < kRing; });
+                    if (stop) return;
+                }
+                const uint64_t b = i * batch, e = b + batch < rows ? b + batch : rows;
+                const int rc = iris_distance_engine_batch_process_resident(engine, ring[i % kRing], e - b, db, b, e);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (rc) {
+                        worker_error = iris_last_error();    // thread-local: capture it on this thread
+                        stop = true;
+                    } else {
+                        produced = i + 1;
+                    }
+                }
+                cv.notify_all();
+                if (rc) return;
+            }
+        });
+        // "Stream output" loop of src/main.rs:437-443
         bool ok = true;
-        for (uint64_t b = 0; ok && b < rows; b += batch) {   // for chunk in patterns.chunks(20_000)
-            const uint64_t e = b + batch < rows ? b + batch : rows;
-            if (iris_distance_engine_batch_process_resident(engine, out.data(), e - b, db, b, e)) die("batch_process");
-            ok = write_all(fd, out.data(), (e - b) * IRIS_ROTATIONS * sizeof(uint16_t));
+        for (uint64_t i = 0; ok && i < n_batches; ++i) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || produced > i; });
+                if (produced <= i) break;                    // the worker failed
+            }
+            const uint64_t b = i * batch, e = b + batch < rows ? b + batch : rows;
+            ok = write_all(fd, ring[i % kRing], (e - b) * IRIS_ROTATIONS * sizeof(uint16_t));
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                consumed = i + 1;
+            }
+            cv.notify_all();
         }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        worker.join();
         iris_distance_engine_free(engine);
         close(fd);                                           // EOF = end of results
+        if (!worker_error.empty()) {
+            fprintf(stderr, "iris_participant: batch_process: %s\n", worker_error.c_str());
+            return 1;
+        }
         fprintf(stderr, ok ? "Reply sent.\n" : "Peer went away.\n");
     }
+    for (uint16_t* slot : ring) iris_host_free(slot);
     close(ls);
     iris_db_destroy(db);
     return 0;
