@@ -10,7 +10,7 @@ use crate::{bits::LIMBS, Bits, EncodedBits, Template, BITS};
 use std::{
     ffi::CStr,
     ops::Range,
-    os::raw::{c_char, c_int},
+    os::raw::{c_char, c_int, c_void},
     ptr,
 };
 
@@ -92,6 +92,15 @@ extern "C" {
         min_distance: *mut f64,
         min_index: *mut u64,
     ) -> c_int;
+    // Page-locked result buffers (instead of a fresh Vec per chunk, main.rs:429, 514) and device buffers.
+    #[allow(dead_code)]
+    fn iris_host_alloc(bytes: u64, out: *mut *mut c_void) -> c_int;
+    #[allow(dead_code)]
+    fn iris_host_free(ptr: *mut c_void) -> c_int;
+    #[allow(dead_code)]
+    fn iris_device_alloc(device: c_int, bytes: u64, out: *mut *mut c_void) -> c_int;
+    #[allow(dead_code)]
+    fn iris_device_free(device: c_int, ptr: *mut c_void) -> c_int;
 }
 
 fn check(rc: c_int) {
