@@ -13,10 +13,11 @@
 // alternate stages (splitting one stage over more warps does not help; measured).
 //
 // What bounds it is the tensor-core side, not HBM: with the expanders switched off (timing experiment) the UMMAs
-// alone take 0.354 ms per 1 M rows -- one M=128, N=32, K=32 kind::i8 instruction per ~31 cycles per SM although
-// its MACs need 16, which matches a 4 KiB A operand entering at 128 B/clk (12.8 GB of expanded operand per 1 M
-// rows).  The complete kernel takes 0.363-0.373 ms alone (0.70 of the HBM roofline).  Multicasting the query
-// operand across a cluster of two halves the L2 reads and changes nothing; details in DESIGN.md 5.3.
+// alone take 0.32-0.36 ms per 1 M rows -- one N=32, K=32 kind::i8 instruction per ~30 cycles per SM although its
+// MACs need 16.  That cost per instruction does not move with M (64 or 128), with the number of accumulators
+// (one or two per tile) or with the number of issuing warps (two or four), so it is a floor of the instruction,
+// and K = 32 bytes and N = 31 rotations are fixed here.  The complete kernel takes 0.363-0.373 ms alone (0.70 of
+// the HBM roofline).  Details and the other experiments (cluster multicast, expander sets) in DESIGN.md 5.3.
 //
 // Per stage: 256 mask bits of 2 x 128 rows = 2 x 4 KiB of packed database (contiguous per tile) + 8 KiB of operand.
 //   producer (warp 4)     : 3 bulk copies into a 12-deep smem ring
