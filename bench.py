@@ -257,10 +257,19 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     out["denominators_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
                                    "algorithmic_GBps": rows * 1662 / (ms * 1e-3) / 1e9,
                                    "sm_mhz": _NVML["last_mhz"],
-                                   "note": "bound by the UMMA operand fetch, not by HBM (DESIGN.md 5.3)"}
+                                   "note": "bound by the per-instruction cost of N = 32 UMMAs, not by HBM (DESIGN.md 5.3)"}
     ms = _time_ms(stream, lambda: iris.match(de, None, db, 0, rows, d_dist, None), db.synchronize, warmup=3, iters=10)
     out["distances_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
                                 "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9, "sm_mhz": _NVML["last_mhz"]}
+    # the general path: a uniform-u16 query (what the reference's criterion bench draws, src/arch/mod.rs:56-61) needs
+    # all three limb products; the headline's ternary encode(Template) query takes the two-product path
+    qu = np.random.default_rng(77).integers(0, 2**16, size=12800, dtype=np.uint16)
+    du = iris.DistanceEngine(qu, device=db.device)
+    ms = _time_ms(stream, lambda: iris.match(du, me, db, 0, rows, d_dist, d_den), db.synchronize, warmup=3, iters=10)
+    out["fused_uniform_u16_query_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
+                                         "algorithmic_GBps": rows * BYTES_PER_ROW_FUSED / (ms * 1e-3) / 1e9,
+                                         "limb_products": 3, "sm_mhz": _NVML["last_mhz"]}
+    du.close()
     # int8 library GEMM on this box: the measured tensor-core denominator
     a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
     b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
