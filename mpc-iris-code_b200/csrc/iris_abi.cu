@@ -33,9 +33,11 @@ static int fail(int code, const char* fmt, ...) {
 #define CK(expr)                                                                                     \
     do {                                                                                             \
         cudaError_t e_ = (expr);                                                                     \
-        if (e_ != cudaSuccess)                                                                       \
+        if (e_ != cudaSuccess) {                                                                     \
+            cudaGetLastError(); /* a non-sticky error must not resurface in a later, unrelated call */ \
             return fail(e_ == cudaErrorMemoryAllocation ? IRIS_ERR_NOMEM : IRIS_ERR_CUDA, "%s failed: %s", #expr, \
                         cudaGetErrorString(e_));                                                     \
+        }                                                                                            \
     } while (0)
 
 struct DeviceGuard {
