@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libiris_b200.so")
-SOURCES = ["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan.cu"]
+SOURCES = ["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan.cu", "iris_maskscan4.cu"]
 HEADERS = ["iris_layout.h", "iris_ptx.cuh", "iris_kernels.cuh", "iris_epilogue.cuh", "../../include/iris_b200.h"]
 
 NVCC_FLAGS = [

@@ -472,6 +472,7 @@ static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t
     p.masks = qm ? db->d_masks : nullptr;
     p.qd = qd;
     p.qm = qm;
+    p.qm4 = qm ? qm + kQmBytes : nullptr;        // every mask operand buffer is [int8 image | 4-bit image]
     p.raw_out = raw_dev;
     p.error = db->d_error;
     p.signed_query = signed_query && !raw_dev;   // the raw dump shows the three-product accumulators
@@ -697,11 +698,12 @@ extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templ
                     m->device = device;
                     r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&m->d_qmask));
                     if (r) return r;
-                    r = pooled_alloc(g_pool.qm, device, kQmBytes, reinterpret_cast<void**>(&m->d_qm));
+                    r = pooled_alloc(g_pool.qm, device, kQmBytes + kQm4Bytes, reinterpret_cast<void**>(&m->d_qm));
                     if (r) return r;
                     CK(cudaMemcpyAsync(m->d_qmask, p.templates + (size_t)i * 2 * IRIS_MASK_BYTES + IRIS_MASK_BYTES, IRIS_MASK_BYTES,
                                        cudaMemcpyDeviceToDevice, cudaStreamPerThread));
                     p.qm[i] = m->d_qm;
+                    CK(launch_prep_mask_query_fp4(m->d_qmask, m->d_qm + kQmBytes, cudaStreamPerThread));
                 }
             }
             CK(launch_prep_batch(p, cudaStreamPerThread));
@@ -749,10 +751,11 @@ extern "C" int iris_masks_engine_new(int device, const uint64_t* query_mask, iri
     auto body = [&]() -> int {
         int r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&e->d_qmask));
         if (r) return r;
-        r = pooled_alloc(g_pool.qm, device, kQmBytes, reinterpret_cast<void**>(&e->d_qm));
+        r = pooled_alloc(g_pool.qm, device, kQmBytes + kQm4Bytes, reinterpret_cast<void**>(&e->d_qm));
         if (r) return r;
         CK(cudaMemcpyAsync(e->d_qmask, query_mask, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
         CK(launch_prep_mask_query(e->d_qmask, e->d_qm, cudaStreamPerThread));
+        CK(launch_prep_mask_query_fp4(e->d_qmask, e->d_qm + kQmBytes, cudaStreamPerThread));
         CK(cudaStreamSynchronize(cudaStreamPerThread));
         return IRIS_OK;
     };

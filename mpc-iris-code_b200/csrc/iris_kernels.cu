@@ -313,14 +313,20 @@ cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
     if (s) return p.signed_query ? launch_scan_t<true, false, true>(p, num_sms, stream)
                                  : launch_scan_t<true, false, false>(p, num_sms, stream);
     if (m) {
-        // denominators only: the TMEM-operand kernel (iris_maskscan.cu); IRIS_MASKSCAN=smem selects the
-        // shared-memory-operand variant of this file (kept for A/B measurements and the raw debug dump)
-        static const bool use_smem = [] {
+        // denominators only: the TMEM-operand kernels -- 4-bit operands (iris_maskscan4.cu) when the engine carries
+        // that image, else int8 (iris_maskscan.cu).  IRIS_MASKSCAN=i8 / smem select the int8 TMEM kernel / the
+        // shared-memory-operand variant of this file (kept for A/B measurements and the raw debug dump).
+        static const char mode = [] {
             const char* e = getenv("IRIS_MASKSCAN");
-            return e && e[0] == 's';
+            return e ? e[0] : 'f';
         }();
-        if (!use_smem && !p.raw_out) return launch_mask_scan(p, num_sms, stream);
-        return launch_scan_t<false, true, false>(p, num_sms, stream);
+        if (mode == 's' || p.raw_out) return launch_scan_t<false, true, false>(p, num_sms, stream);
+        if (mode != 'i' && p.qm4) {
+            ScanParams p4 = p;
+            p4.qm = p.qm4;
+            return launch_mask_scan_fp4(p4, num_sms, stream);
+        }
+        return launch_mask_scan(p, num_sms, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -12,6 +12,7 @@ struct ScanParams {
     const uint8_t* masks;    // tiled packed masks (nullptr when not scanning denominators)
     const uint8_t* qd;       // prepared distance operand image (kQdBytes)
     const uint8_t* qm;       // prepared mask operand image (kQmBytes)
+    const uint8_t* qm4;      // 4-bit mask operand image (kQm4Bytes) for the denominators-only scan, or nullptr
     uint16_t* dist_out;      // [row_end-row_begin][31] u16, row-major packed (62 B rows)
     uint16_t* den_out;       // same
     int32_t* raw_out;        // optional debug dump: [tiles*128][128] raw s32 accumulators
@@ -27,6 +28,9 @@ struct ScanParams {
 cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
 // Denominators-only scan with the expanded operand in tensor memory (iris_maskscan.cu).
 cudaError_t launch_mask_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
+// The same scan with e2m1 operands (kind::mxf4, iris_maskscan4.cu); p.qm must be the 4-bit image.
+cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_prep_mask_query_fp4(const uint8_t* d_qmask, uint8_t* d_qm4, cudaStream_t stream);
 
 // Query preparation (K3): reference DistanceEngine::new / MasksEngine::new (src/lib.rs:33-40, 60-67).
 cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint16_t* d_out, cudaStream_t stream);

@@ -43,6 +43,8 @@ constexpr size_t kShareTileBytes = (size_t)kChunks * kShareChunkBytes;   // 3,27
 constexpr size_t kMaskTileBytes = (size_t)kChunks * kMaskChunkBytes;     // 204,800   = 128 * 1600
 constexpr size_t kQdBytes = (size_t)kChunks * kQdChunkBytes;             // 819,200
 constexpr size_t kQmBytes = (size_t)kChunks * kQmChunkBytes;             // 409,600
+constexpr int kQm4StageBytes = 32 * 128;                                 // 4-bit mask operand: 32 rotations x 256 nibbles
+constexpr size_t kQm4Bytes = (size_t)(IRIS_BITS / 256) * kQm4StageBytes; // 204,800
 constexpr int kOutRowBytes = IRIS_ROTATIONS * 2;                         // 62
 
 __host__ __device__ inline uint32_t swz128(uint32_t r, uint32_t b) {
