@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 
 #include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
@@ -41,14 +43,13 @@ constexpr int kM4PkBytes = kM4StageBits / 8 * kTileRows;          // 4 KiB of pa
 constexpr int kM4QBytes = kQm4StageBytes;                         // 4 KiB: 32 rotations x 256 nibbles
 constexpr int kM4OffQ = kM4Tiles * kM4PkBytes;
 constexpr int kM4StageBytes = kM4OffQ + kM4QBytes;                // 12 KiB
-constexpr int kM4Stages = 12;
 constexpr int kM4ARing = 5;                                       // TMEM A slots of 2 tiles x 32 columns
 constexpr int kM4OutStageBytes = 8192;
-constexpr int kM4SmemBytes = 1024 + kM4Stages * kM4StageBytes + kM4OutStageBytes + 512;
-constexpr int kM4IssuerWarp0 = 5;                                 // warps 5, 6
-constexpr int kM4ExpWarp0 = 7;                                    // expander warps: [set][tile][TMEM lane quadrant]
-constexpr int kM4ExpSets = 2;
-constexpr int kM4Threads = (kM4ExpWarp0 + kM4ExpSets * 4 * kM4Tiles) * 32;     // 736
+constexpr int kM4BarBytes = 1024;
+constexpr int m4_smem_bytes(int stages) { return 1024 + stages * kM4StageBytes + kM4OutStageBytes + kM4BarBytes; }
+constexpr int kM4IssuerWarp0 = 5;                                 // issuer warps: [k-parity][tile]
+constexpr int m4_exp_warp0(int iss) { return kM4IssuerWarp0 + iss * kM4Tiles; }   // expander warps: [set][tile][TMEM lane quadrant]
+constexpr int m4_threads(int sets, int iss) { return (m4_exp_warp0(iss) + sets * 4 * kM4Tiles) * 32; }   // 736 for 2 sets, 1 issuer per tile
 constexpr uint32_t kM4AccCols = 2 * kM4Tiles * 32;                // [buffer][tile] x 32 f32 columns
 constexpr uint32_t kM4SfCol = kM4AccCols;                         // 32 columns of 0x7F scale-factor bytes
 constexpr uint32_t kM4ACol = kM4SfCol + 32;
@@ -57,7 +58,6 @@ constexpr uint32_t kM4TmemCols = 512;
 static_assert(IRIS_BITS % kM4StageBits == 0, "stages must tile the K dimension");
 static_assert(kM4StageBits == 2 * 8 * kMaskChunkBytes / kTileRows, "a stage is two 128-bit mask chunks");
 static_assert(kM4ACol + kM4ARing * kM4ASlotCols <= kM4TmemCols, "TMEM budget");
-static_assert(kM4SmemBytes <= 232448, "exceeds 227 KiB of shared memory");
 static_assert(kM4StageBytes % 1024 == 0 && kM4OffQ % 1024 == 0, "operand tiles must stay 1024-byte aligned");
 
 enum M4Watchdog { kW4Producer = 501, kW4MmaFull = 502, kW4MmaA = 503, kW4MmaTmem = 504, kW4ExpFull = 505, kW4ExpA = 506, kW4Epilogue = 507 };
@@ -90,21 +90,36 @@ constexpr uint32_t kM4Idesc = (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | (1u 
 constexpr uint32_t kM4DescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
 
 // p.qm is the 4-bit operand image here (kQm4Bytes); p.tile_begin / p.tile_end as in mask_scan_kernel.
-__global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const ScanParams p) {
+// kSets: expander warp sets taking alternate stages.  kIss: issuing warps per row tile; with two, each takes every
+// second stage into its own accumulator (the epilogue adds them) and the accumulators are single-buffered.
+// kFlags (A/B switches): 2 / 4 = timing only, no expansion / no UMMAs (wrong results); 32 = expand into registers
+// before waiting for the TMEM slot; 256 = per-role wait-time profile of CTA 0 (device printf).
+template <int kSets, int kIss, int kFlags, int kStages>
+__global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kernel(const ScanParams p) {
+    static_assert(kSets <= kM4ARing && kSets <= kStages && kIss <= 2, "ring positions advance with at most one wrap");
+    static_assert(m4_smem_bytes(kStages) <= 232448, "exceeds 227 KiB of shared memory");
+    static_assert(m4_threads(kSets, kIss) <= 1024, "too many warps");
+    static_assert(kM4StagesPerTile % kIss == 0, "every issuer takes the same number of stages per tile");
+    constexpr int kExpWarp0 = m4_exp_warp0(kIss);
+    constexpr int kAccBufs = kIss == 1 ? 2 : 1;                     // accumulator sets: [buffer][tile][issuer] x 32 columns
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* const base_ptr = smem_raw + (base - raw_addr);
-    uint8_t* const out_stage_ptr = base_ptr + kM4Stages * kM4StageBytes;
-    const uint32_t bars = base + kM4Stages * kM4StageBytes + kM4OutStageBytes;
+    uint8_t* const out_stage_ptr = base_ptr + kStages * kM4StageBytes;
+    const uint32_t bars = base + kStages * kM4StageBytes + kM4OutStageBytes;
     auto full_bar = [&](int s) { return bars + 8u * s; };                                   // stage landed (tx)
-    auto empty_bar = [&](int s) { return bars + 8u * (kM4Stages + s); };                    // 8 expander warps + 2 issuer commits
-    auto afull_bar = [&](int a, int t) { return bars + 8u * (2 * kM4Stages + 2 * a + t); };                 // 4 expander warps of tile t
-    auto aempty_bar = [&](int a, int t) { return bars + 8u * (2 * kM4Stages + 2 * kM4ARing + 2 * a + t); }; // issuer t commit
-    auto tfull_bar = [&](int b, int t) { return bars + 8u * (2 * kM4Stages + 4 * kM4ARing + 2 * b + t); };
-    auto tempty_bar = [&](int b, int t) { return bars + 8u * (2 * kM4Stages + 4 * kM4ARing + 4 + 2 * b + t); };
-    constexpr int kNumBars = 2 * kM4Stages + 4 * kM4ARing + 8;
-    static_assert(8 * (kNumBars + 1) <= 512, "barrier table");
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };                    // 8 expander warps + 2 issuer commits
+    // The TMEM A ring has kM4ARing slots but 2 * kM4ARing barriers per direction: stage g uses slot g % kM4ARing and
+    // barrier j = g % (2 * kM4ARing), so that each barrier always pairs the same expander set with the same issuing
+    // warp (stages of one parity) and nobody ever waits on a phase two uses ahead.
+    auto afull_bar = [&](int j, int t) { return bars + 8u * (2 * kStages + 2 * j + t); };                 // 4 expander warps of tile t
+    auto aempty_bar = [&](int j, int t) { return bars + 8u * (2 * kStages + 4 * kM4ARing + 2 * j + t); }; // one commit
+    auto tfull_bar = [&](int b, int t) { return bars + 8u * (2 * kStages + 8 * kM4ARing + 2 * b + t); };
+    auto tempty_bar = [&](int b, int t) { return bars + 8u * (2 * kStages + 8 * kM4ARing + 4 + 2 * b + t); };
+    constexpr int kNumBars = 2 * kStages + 8 * kM4ARing + 8;
+    constexpr int kABars = 2 * kM4ARing;
+    static_assert(8 * (kNumBars + 1) <= kM4BarBytes, "barrier table");
     const uint32_t tmem_slot = bars + 8u * kNumBars;
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(out_stage_ptr + kM4OutStageBytes + 8 * kNumBars);
@@ -113,18 +128,18 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kM4Stages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), 4 * kM4Tiles + kM4Tiles);
+            ptx::mbar_init(empty_bar(s), 4 * kM4Tiles + kM4Tiles);     // expander warps + one commit per tile
         }
-        for (int a = 0; a < kM4ARing; ++a)
+        for (int a = 0; a < kABars; ++a)
             for (int t = 0; t < kM4Tiles; ++t) {
                 ptx::mbar_init(afull_bar(a, t), 4);
                 ptx::mbar_init(aempty_bar(a, t), 1);
             }
         for (int b = 0; b < 2; ++b)
             for (int t = 0; t < kM4Tiles; ++t) {
-                ptx::mbar_init(tfull_bar(b, t), 1);
+                ptx::mbar_init(tfull_bar(b, t), kIss);
                 ptx::mbar_init(tempty_bar(b, t), 4);
             }
         ptx::fence_mbar_init();
@@ -145,6 +160,12 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
     __syncthreads();
     ptx::tc_fence_after();
 
+    // kFlags & 256: per-role wait-time profile of CTA 0 (device printf at the end)
+    constexpr bool kProf = (kFlags & 256) != 0;
+    long long prof[4] = {0, 0, 0, 0};
+    const long long prof_t0 = kProf ? clock64() : 0;
+#define M4_TIMED(slot, stmt) do { if (kProf) { const long long t_ = clock64(); stmt; prof[slot] += clock64() - t_; } else { stmt; } } while (0)
+
     const uint32_t pair_begin = p.tile_begin / kM4Tiles;
     const uint32_t pair_end = (p.tile_end + kM4Tiles - 1) / kM4Tiles;
     const uint32_t pair0 = pair_begin + blockIdx.x;
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
             const uint8_t* mk = p.masks + (size_t)pair * kM4Tiles * kMaskTileBytes;
             for (int c = 0; c < kM4StagesPerTile; ++c) {
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kW4Producer);
+                M4_TIMED(0, ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kW4Producer));
                 const uint32_t sbase = base + stage * kM4StageBytes;
                 const uint32_t fb = full_bar(stage);
                 if (ptx::elect_one_sync()) {
@@ -171,82 +192,111 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
                     ptx::bulk_g2s_hint(sbase + kM4OffQ, p.qm + (size_t)c * kM4QBytes, kM4QBytes, fb, pol_keep);
                 }
                 __syncwarp();
-                if (++stage == kM4Stages) { stage = 0; phase ^= 1u; }
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == kM4IssuerWarp0 || warp == kM4IssuerWarp0 + 1) {
-        // ------------------------------------------------------------------ UMMA issuers: one warp per row tile
-        const int t = warp - kM4IssuerWarp0;
+    } else if (warp >= kM4IssuerWarp0 && warp < kExpWarp0) {
+        // ------------------------------------------------------------------ UMMA issuers
+        // warp (par, t) issues the stages g = par (mod kIss) of row tile t into its own accumulator
+        const int t = (warp - kM4IssuerWarp0) % kM4Tiles;
+        const int par = (warp - kM4IssuerWarp0) / kM4Tiles;
         const uint32_t sf = tmem_base + kM4SfCol;
-        int stage = 0, ar = 0;
-        uint32_t phase = 0, aphase = 0, it = 0;
-        for (uint32_t pair = pair0; pair < pair_end; pair += pair_step, ++it) {
-            const uint32_t buf = it & 1u;
-            ptx::mbar_wait(tempty_bar(buf, t), ((it >> 1) & 1u) ^ 1u, p.error, kW4MmaTmem);
-            ptx::tc_fence_after();
-            const uint32_t d = tmem_base + buf * (kM4Tiles * 32u) + t * 32u;
-            for (int c = 0; c < kM4StagesPerTile; ++c) {
-                ptx::mbar_wait(full_bar(stage), phase, p.error, kW4MmaFull);
-                ptx::mbar_wait(afull_bar(ar, t), aphase, p.error, kW4MmaA);
+        const uint32_t my_pairs = pair0 < pair_end ? (pair_end - pair0 + pair_step - 1) / pair_step : 0;
+        const uint32_t total = my_pairs * kM4StagesPerTile;
+        int stage = par, aj = par, c = par;         // ring positions and stage-within-tile of g
+        uint32_t phase = 0, aphase = 0, it = 0, d = 0;
+        for (uint32_t g = par; g < total; g += kIss) {
+            if (c == par) {                          // first stage of a tile: the accumulator must have been drained
+                const uint32_t buf = kAccBufs == 2 ? (it & 1u) : 0u;
+                const uint32_t par_t = kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
+                M4_TIMED(2, ptx::mbar_wait(tempty_bar(buf, t), par_t ^ 1u, p.error, kW4MmaTmem));
                 ptx::tc_fence_after();
-                const uint32_t qbase = base + stage * kM4StageBytes + kM4OffQ;
-                const uint32_t abase = tmem_base + kM4ACol + ar * kM4ASlotCols + t * 32u;
-                const uint32_t blo0 = ((qbase & 0x3FFFFu) >> 4) | (1u << 16);
-                if (ptx::elect_one_sync()) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
-                        umma_mxf4_ts(d, abase + k * 8, blo0 + ((32 * k) >> 4), kM4DescHiSw128, kM4Idesc, sf,
-                                     k ? 1u : (c ? 1u : 0u));
-                    ptx::umma_commit(aempty_bar(ar, t));
-                    ptx::umma_commit(empty_bar(stage));
-                    if (c == kM4StagesPerTile - 1) ptx::umma_commit(tfull_bar(buf, t));
-                }
-                __syncwarp();
-                if (++stage == kM4Stages) { stage = 0; phase ^= 1u; }
-                if (++ar == kM4ARing) { ar = 0; aphase ^= 1u; }
+                d = tmem_base + ((buf * kM4Tiles + t) * kIss + par) * 32u;
             }
+            M4_TIMED(0, ptx::mbar_wait(full_bar(stage), phase, p.error, kW4MmaFull));
+            M4_TIMED(1, ptx::mbar_wait(afull_bar(aj, t), aphase, p.error, kW4MmaA));
+            const int ar = aj >= kM4ARing ? aj - kM4ARing : aj;
+            ptx::tc_fence_after();
+            const uint32_t qbase = base + stage * kM4StageBytes + kM4OffQ;
+            const uint32_t abase = tmem_base + kM4ACol + ar * kM4ASlotCols + t * 32u;
+            const uint32_t blo0 = ((qbase & 0x3FFFFu) >> 4) | (1u << 16);
+            const bool last = c + kIss >= kM4StagesPerTile;
+            if (ptx::elect_one_sync()) {
+#pragma unroll
+                for (int k = 0; k < ((kFlags & 4) ? 0 : 4); ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
+                    umma_mxf4_ts(d, abase + k * 8, blo0 + ((32 * k) >> 4), kM4DescHiSw128, kM4Idesc, sf,
+                                 k ? 1u : (c != par ? 1u : 0u));
+                ptx::umma_commit(aempty_bar(aj, t));
+                ptx::umma_commit(empty_bar(stage));
+                if (last) ptx::umma_commit(tfull_bar(kAccBufs == 2 ? (it & 1u) : 0u, t));
+            }
+            __syncwarp();
+            stage += kIss;
+            if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
+            aj += kIss;
+            if (aj >= kABars) { aj -= kABars; aphase ^= 1u; }
+            c += kIss;
+            if (c >= kM4StagesPerTile) { c -= kM4StagesPerTile; ++it; }
         }
-    } else if (warp >= kM4ExpWarp0) {
+    } else if (warp >= kExpWarp0) {
         // ------------------------------------------------------------------ expanders: packed bits -> e2m1 A operand
-        const int set = (warp - kM4ExpWarp0) / (4 * kM4Tiles);      // which stages (g % kM4ExpSets) this warp expands
-        const int t = ((warp - kM4ExpWarp0) >> 2) % kM4Tiles;       // row tile of this warp
+        const int set = (warp - kExpWarp0) / (4 * kM4Tiles);      // this warp expands the stages g = set (mod kSets)
+        const int t = ((warp - kExpWarp0) >> 2) % kM4Tiles;       // row tile of this warp
         const int quad = warp & 3;                                  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        int stage = 0, ar = 0;
-        uint32_t phase = 0, aphase = 0, g = 0;
-        for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
-            for (int c = 0; c < kM4StagesPerTile; ++c, ++g) {
-                if ((int)(g % kM4ExpSets) != set) {       // the other set's stage: only keep the ring state in step
-                    if (++stage == kM4Stages) { stage = 0; phase ^= 1u; }
-                    if (++ar == kM4ARing) { ar = 0; aphase ^= 1u; }
-                    continue;
+        const uint32_t my_pairs = pair0 < pair_end ? (pair_end - pair0 + pair_step - 1) / pair_step : 0;
+        const uint32_t total = my_pairs * kM4StagesPerTile;         // stages of this CTA, all pairs
+        int stage = set, aj = set;
+        uint32_t phase = 0, aphase = 0;
+        {
+            for (uint32_t g = set; g < total; g += kSets) {
+                // the slot was last used by stage g - kM4ARing: its commit went to barrier (aj + kM4ARing) % kABars
+                const int ar = aj >= kM4ARing ? aj - kM4ARing : aj;
+                const int jw = aj >= kM4ARing ? aj - kM4ARing : aj + kM4ARing;
+                const uint32_t wpar = aj >= kM4ARing ? aphase : aphase ^ 1u;
+                M4_TIMED(0, ptx::mbar_wait(full_bar(stage), phase, p.error, kW4ExpFull));
+                if (!(kFlags & 32)) {
+                    M4_TIMED(1, ptx::mbar_wait(aempty_bar(jw, t), wpar, p.error, kW4ExpA));
+                    ptx::tc_fence_after();
                 }
-                ptx::mbar_wait(full_bar(stage), phase, p.error, kW4ExpFull);
-                ptx::mbar_wait(aempty_bar(ar, t), aphase ^ 1u, p.error, kW4ExpA);
-                ptx::tc_fence_after();
-                const uint8_t* pk = base_ptr + stage * kM4StageBytes + t * kM4PkBytes;
-                const uint4 x0 = *reinterpret_cast<const uint4*>(pk + row * 16);                       // bits 0..127
-                const uint4 x1 = *reinterpret_cast<const uint4*>(pk + kMaskChunkBytes + row * 16);     // bits 128..255
-                const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 uint32_t v[32];
+                if (!(kFlags & 2)) {
+                    const uint8_t* pk = base_ptr + stage * kM4StageBytes + t * kM4PkBytes;
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(pk + row * 16);                       // bits 0..127
+                    const uint4 x1 = *reinterpret_cast<const uint4*>(pk + kMaskChunkBytes + row * 16);     // bits 128..255
+                    const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                    v[4 * w + 0] = xs[w] & 0x11111111u;             // 0.5
-                    v[4 * w + 1] = xs[w] & 0x22222222u;             // 1.0
-                    v[4 * w + 2] = xs[w] & 0x44444444u;             // 2.0
-                    v[4 * w + 3] = (xs[w] >> 1) & 0x44444444u;      // bit 3 of each nibble, moved off the sign: 2.0
+                    for (int w = 0; w < 8; ++w) {
+                        v[4 * w + 0] = xs[w] & 0x11111111u;             // 0.5
+                        v[4 * w + 1] = xs[w] & 0x22222222u;             // 1.0
+                        v[4 * w + 2] = xs[w] & 0x44444444u;             // 2.0
+                        v[4 * w + 3] = (xs[w] >> 1) & 0x44444444u;      // bit 3 of each nibble, moved off the sign: 2.0
+                    }
                 }
-                tmem_st32_m4(tmem_base + lane_addr + kM4ACol + ar * kM4ASlotCols + t * 32u, v);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (kFlags & 32) {
+                    // the expanded words are in registers: hand the packed bytes back, then wait for the TMEM slot
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));     // keep the logic ops above the wait
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(empty_bar(stage));
+                    M4_TIMED(1, ptx::mbar_wait(aempty_bar(jw, t), wpar, p.error, kW4ExpA));
+                    ptx::tc_fence_after();
+                }
+                if (!(kFlags & 2)) {
+                    tmem_st32_m4(tmem_base + lane_addr + kM4ACol + ar * kM4ASlotCols + t * 32u, v);
+                    M4_TIMED(2, asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"));
+                }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::mbar_arrive(afull_bar(ar, t));
-                    ptx::mbar_arrive(empty_bar(stage));   // this warp no longer needs the packed bytes
+                    ptx::mbar_arrive(afull_bar(aj, t));
+                    if (!(kFlags & 32)) ptx::mbar_arrive(empty_bar(stage));   // this warp no longer needs the packed bytes
                 }
-                if (++stage == kM4Stages) { stage = 0; phase ^= 1u; }
-                if (++ar == kM4ARing) { ar = 0; aphase ^= 1u; }
+                stage += kSets;
+                if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
+                aj += kSets;
+                if (aj >= kABars) { aj -= kABars; aphase ^= 1u; }
             }
         }
     } else {
@@ -254,12 +304,13 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
         const int row = threadIdx.x;
         uint32_t it = 0;
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step, ++it) {
-            const uint32_t buf = it & 1u;
+            const uint32_t buf = kAccBufs == 2 ? (it & 1u) : 0u;
+            const uint32_t par_t = kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
 #pragma unroll 1
             for (int t = 0; t < kM4Tiles; ++t) {
-                ptx::mbar_wait(tfull_bar(buf, t), (it >> 1) & 1u, p.error, kW4Epilogue);
+                M4_TIMED(0, ptx::mbar_wait(tfull_bar(buf, t), par_t, p.error, kW4Epilogue));
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (kM4Tiles * 32u) + t * 32u;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * kM4Tiles + t) * kIss * 32u;
                 const int64_t trow0 = ((int64_t)pair * kM4Tiles + t) * kTileRows;
                 int64_t lo = (int64_t)p.row_begin - trow0, hi = (int64_t)p.row_end - trow0;
                 const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
@@ -268,6 +319,13 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
                 uint32_t a[32];
                 ptx::tmem_ld32(taddr, a);
                 ptx::tmem_wait_ld();
+                if (kIss == 2) {                    // the other issuer's partial sums (f32, exact)
+                    uint32_t b2[32];
+                    ptx::tmem_ld32(taddr + 32u, b2);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b2[j]));
+                }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(buf, t));
@@ -285,27 +343,51 @@ __global__ void __launch_bounds__(kM4Threads, 1) mask_scan_fp4_kernel(const Scan
         }
     }
 
+    if (kProf && blockIdx.x == 0 && lane == 0)
+        printf("m4prof warp %2d total %lld w0 %lld w1 %lld w2 %lld\n", warp, clock64() - prof_t0, prof[0], prof[1], prof[2]);
+#undef M4_TIMED
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == kM4IssuerWarp0) ptx::tmem_dealloc(tmem_base, kM4TmemCols);
 }
 
-cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t stream) {
+template <int kSets, int kIss, int kFlags, int kStages>
+static cudaError_t launch_m4_t(const ScanParams& p, int num_sms, cudaStream_t stream) {
     static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(mask_scan_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kM4SmemBytes);
+        e = cudaFuncSetAttribute(mask_scan_fp4_kernel<kSets, kIss, kFlags, kStages>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, m4_smem_bytes(kStages));
         if (e != cudaSuccess) return e;
         if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     if (p.tile_end <= p.tile_begin) return cudaSuccess;
     const uint32_t pairs = (p.tile_end + kM4Tiles - 1) / kM4Tiles - p.tile_begin / kM4Tiles;
     const uint32_t grid = pairs < (uint32_t)num_sms ? pairs : (uint32_t)num_sms;
-    mask_scan_fp4_kernel<<<grid, kM4Threads, kM4SmemBytes, stream>>>(p);
+    mask_scan_fp4_kernel<kSets, kIss, kFlags, kStages>
+        <<<grid, m4_threads(kSets, kIss), m4_smem_bytes(kStages), stream>>>(p);
     count_launch_external();
     return cudaGetLastError();
+}
+
+cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t stream) {
+    // IRIS_M4_VARIANT = "<sets><issuers per tile><flags, 3 digits>" selects an A/B variant (diagnostics).
+    static const int variant = [] {
+        const char* e = getenv("IRIS_M4_VARIANT");
+        return e ? atoi(e) : 21000;
+    }();
+    switch (variant) {
+        case 22000: return launch_m4_t<2, 2, 0, 12>(p, num_sms, stream);
+        case 22032: return launch_m4_t<2, 2, 32, 12>(p, num_sms, stream);
+        case 21032: return launch_m4_t<2, 1, 32, 12>(p, num_sms, stream);
+        case 22256: return launch_m4_t<2, 2, 256, 12>(p, num_sms, stream);
+        case 22288: return launch_m4_t<2, 2, 288, 12>(p, num_sms, stream);
+        case 22002: return launch_m4_t<2, 2, 2, 12>(p, num_sms, stream);
+        case 22004: return launch_m4_t<2, 2, 4, 12>(p, num_sms, stream);
+        default: return launch_m4_t<2, 1, 0, 12>(p, num_sms, stream);
+    }
 }
 
 // Query operand image for mask_scan_fp4_kernel: [stage s < 50][rotation slot r < 32][128 B, SWIZZLE_128B]; the 16-byte

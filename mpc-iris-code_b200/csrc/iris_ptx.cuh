@@ -64,13 +64,37 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // never as a hung GPU.  `code` identifies the waiting role.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
     if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FF) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+    uint64_t t0 = 0;
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 1024; ++i)          // the poll loop proper: no timer read in it
+            if (mbar_try_wait(bar, parity)) return;
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ull) {
             if (err) atomicExch(err, code);
             __threadfence_system();
             __trap();
+        }
+    }
+}
+
+// Same, for roles off the critical path (epilogue, producer): sleep between polls so the spinning warp
+// leaves its scheduler's issue slots to the working warps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if ((++spins & 0x3FF) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) {
+                if (err) atomicExch(err, code);
+                __threadfence_system();
+                __trap();
+            }
         }
     }
 }
