@@ -89,59 +89,58 @@ __device__ __forceinline__ void umma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, u
 constexpr uint32_t kM4Idesc = (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
 constexpr uint32_t kM4DescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
 
-// p.qm is the 4-bit operand image here (kQm4Bytes); p.tile_begin / p.tile_end as in mask_scan_kernel.
-// kSets: expander warp sets taking alternate stages.  kIss: issuing warps per row tile; with two, each takes every
-// second stage into its own accumulator (the epilogue adds them) and the accumulators are single-buffered.
-// kFlags (A/B switches): 2 / 4 = timing only, no expansion / no UMMAs (wrong results); 32 = expand into registers
-// before waiting for the TMEM slot; 256 = per-role wait-time profile of CTA 0 (device printf).
-template <int kSets, int kIss, int kFlags, int kStages>
-__global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kernel(const ScanParams p) {
-    static_assert(kSets <= kM4ARing && kSets <= kStages && kIss <= 2, "ring positions advance with at most one wrap");
-    static_assert(m4_smem_bytes(kStages) <= 232448, "exceeds 227 KiB of shared memory");
-    static_assert(m4_threads(kSets, kIss) <= 1024, "too many warps");
-    static_assert(kM4StagesPerTile % kIss == 0, "every issuer takes the same number of stages per tile");
-    constexpr int kExpWarp0 = m4_exp_warp0(kIss);
-    constexpr int kAccBufs = kIss == 1 ? 2 : 1;                     // accumulator sets: [buffer][tile][issuer] x 32 columns
+// ---------------------------------------------------------------------------------------------------------
+// Period-unrolled kernel (the product path).  Rings: 10 smem stages, 5 TMEM A slots with 10 barriers per direction
+// (stage g uses slot g % 5 and barrier g % 10, so a barrier always pairs the same expander set with the same issuing
+// warp and nobody waits on a phase two uses ahead).  Two expander sets and two issuing warps per tile each take the
+// stages of one parity, so for every role the ring state repeats after 5 visits (= 10 stages = one revolution of
+// both rings): the role loops are unrolled over that period and every barrier / slot / descriptor offset is an
+// immediate.  The issuing warps' instruction stream is what paces this kernel (tests/diagnostics/umma_bench.cu: a
+// TS-form N = 32 UMMA retires every 16 cycles when issued back to back), hence two of them per tile, each with its
+// own accumulator (the epilogue adds the two partial sums; f32, exact).
+// kFlags (diagnostics): 2 / 4 = timing only, no expansion / no UMMAs (wrong results); 256 = per-role wait profile.
+constexpr int kP4Stages = 10;
+constexpr int kP4ABars = 2 * kM4ARing;
+constexpr int kP4Period = 5;                                      // visits per role and revolution
+constexpr int kP4IssWarps = 2 * kM4Tiles;                         // [parity][tile]
+constexpr int kP4ExpWarp0 = kM4IssuerWarp0 + kP4IssWarps;         // 9: [set][tile][TMEM lane quadrant]
+constexpr int kP4Threads = (kP4ExpWarp0 + 2 * 4 * kM4Tiles) * 32; // 800
+constexpr int kP4SmemBytes = m4_smem_bytes(kP4Stages);
+static_assert(kP4Stages == kP4ABars && kP4Stages == 2 * kP4Period, "one revolution of both rings per period");
+static_assert(kM4StagesPerTile % kP4Stages == 0, "a tile is a whole number of revolutions");
+static_assert(kP4SmemBytes <= 232448, "exceeds 227 KiB of shared memory");
+
+template <int kFlags>
+__global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const ScanParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* const base_ptr = smem_raw + (base - raw_addr);
-    uint8_t* const out_stage_ptr = base_ptr + kStages * kM4StageBytes;
-    const uint32_t bars = base + kStages * kM4StageBytes + kM4OutStageBytes;
-    auto full_bar = [&](int s) { return bars + 8u * s; };                                   // stage landed (tx)
-    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };                    // 8 expander warps + 2 issuer commits
-    // The TMEM A ring has kM4ARing slots but 2 * kM4ARing barriers per direction: stage g uses slot g % kM4ARing and
-    // barrier j = g % (2 * kM4ARing), so that each barrier always pairs the same expander set with the same issuing
-    // warp (stages of one parity) and nobody ever waits on a phase two uses ahead.
-    auto afull_bar = [&](int j, int t) { return bars + 8u * (2 * kStages + 2 * j + t); };                 // 4 expander warps of tile t
-    auto aempty_bar = [&](int j, int t) { return bars + 8u * (2 * kStages + 4 * kM4ARing + 2 * j + t); }; // one commit
-    auto tfull_bar = [&](int b, int t) { return bars + 8u * (2 * kStages + 8 * kM4ARing + 2 * b + t); };
-    auto tempty_bar = [&](int b, int t) { return bars + 8u * (2 * kStages + 8 * kM4ARing + 4 + 2 * b + t); };
-    constexpr int kNumBars = 2 * kStages + 8 * kM4ARing + 8;
-    constexpr int kABars = 2 * kM4ARing;
-    static_assert(8 * (kNumBars + 1) <= kM4BarBytes, "barrier table");
-    const uint32_t tmem_slot = bars + 8u * kNumBars;
-    volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(out_stage_ptr + kM4OutStageBytes + 8 * kNumBars);
+    uint8_t* const out_stage_ptr = base_ptr + kP4Stages * kM4StageBytes;
+    const uint32_t bars = base + kP4Stages * kM4StageBytes + kM4OutStageBytes;
+    // barrier table (8 bytes each): full[10] empty[10] afull[10][2] aempty[10][2] tfull[2] tempty[2]
+    constexpr uint32_t kFull = 0, kEmpty = 8 * kP4Stages, kAFull = 16 * kP4Stages, kAEmpty = kAFull + 16 * kP4ABars,
+                       kTFull = kAEmpty + 16 * kP4ABars, kTEmpty = kTFull + 16, kBarEnd = kTEmpty + 16;
+    static_assert(kBarEnd + 8 <= kM4BarBytes, "barrier table");
+    const uint32_t tmem_slot = bars + kBarEnd;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(out_stage_ptr + kM4OutStageBytes + kBarEnd);
 
     const int warp = ptx::warp_idx_sync();      // warp-uniform role index
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), 4 * kM4Tiles + kM4Tiles);     // expander warps + one commit per tile
+        for (int s = 0; s < kP4Stages; ++s) {
+            ptx::mbar_init(bars + kFull + 8 * s, 1);
+            ptx::mbar_init(bars + kEmpty + 8 * s, 4 * kM4Tiles + kM4Tiles);     // expander warps + one commit per tile
         }
-        for (int a = 0; a < kABars; ++a)
-            for (int t = 0; t < kM4Tiles; ++t) {
-                ptx::mbar_init(afull_bar(a, t), 4);
-                ptx::mbar_init(aempty_bar(a, t), 1);
-            }
-        for (int b = 0; b < 2; ++b)
-            for (int t = 0; t < kM4Tiles; ++t) {
-                ptx::mbar_init(tfull_bar(b, t), kIss);
-                ptx::mbar_init(tempty_bar(b, t), 4);
-            }
+        for (int j = 0; j < kP4ABars * kM4Tiles; ++j) {
+            ptx::mbar_init(bars + kAFull + 8 * j, 4);                            // 4 expander warps of one tile
+            ptx::mbar_init(bars + kAEmpty + 8 * j, 1);                           // the issuing warp's commit
+        }
+        for (int t = 0; t < kM4Tiles; ++t) {
+            ptx::mbar_init(bars + kTFull + 8 * t, 2);                            // both issuing warps of the tile
+            ptx::mbar_init(bars + kTEmpty + 8 * t, 4);                           // epilogue warps
+        }
         ptx::fence_mbar_init();
     }
     if (warp == kM4IssuerWarp0) ptx::tmem_alloc(tmem_slot, kM4TmemCols);
@@ -160,9 +159,8 @@ __global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kern
     __syncthreads();
     ptx::tc_fence_after();
 
-    // kFlags & 256: per-role wait-time profile of CTA 0 (device printf at the end)
     constexpr bool kProf = (kFlags & 256) != 0;
-    long long prof[4] = {0, 0, 0, 0};
+    long long prof[3] = {0, 0, 0};
     const long long prof_t0 = kProf ? clock64() : 0;
 #define M4_TIMED(slot, stmt) do { if (kProf) { const long long t_ = clock64(); stmt; prof[slot] += clock64() - t_; } else { stmt; } } while (0)
 
@@ -170,101 +168,95 @@ __global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kern
     const uint32_t pair_end = (p.tile_end + kM4Tiles - 1) / kM4Tiles;
     const uint32_t pair0 = pair_begin + blockIdx.x;
     const uint32_t pair_step = gridDim.x;
+    const uint32_t my_pairs = pair0 < pair_end ? (pair_end - pair0 + pair_step - 1) / pair_step : 0;
+    constexpr int kRevsPerTile = kM4StagesPerTile / kP4Stages;     // 5
 
     if (warp == 4) {
         // ------------------------------------------------------------------ producer
         const uint64_t pol_stream = ptx::policy_evict_first();
         const uint64_t pol_keep = ptx::policy_evict_last();
-        int stage = 0;
-        uint32_t phase = 0;
+        uint32_t ph = 0;
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
             const uint8_t* mk = p.masks + (size_t)pair * kM4Tiles * kMaskTileBytes;
-            for (int c = 0; c < kM4StagesPerTile; ++c) {
-                M4_TIMED(0, ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kW4Producer));
-                const uint32_t sbase = base + stage * kM4StageBytes;
-                const uint32_t fb = full_bar(stage);
-                if (ptx::elect_one_sync()) {
-                    ptx::mbar_arrive_expect_tx(fb, kM4StageBytes);
+            for (int rev = 0; rev < kRevsPerTile; ++rev, ph ^= 1u) {
 #pragma unroll
-                    for (int t = 0; t < kM4Tiles; ++t)
-                        ptx::bulk_g2s_hint(sbase + t * kM4PkBytes, mk + (size_t)t * kMaskTileBytes + (size_t)c * kM4PkBytes,
-                                           kM4PkBytes, fb, pol_stream);
-                    ptx::bulk_g2s_hint(sbase + kM4OffQ, p.qm + (size_t)c * kM4QBytes, kM4QBytes, fb, pol_keep);
+                for (int s = 0; s < kP4Stages; ++s) {
+                    const int c = rev * kP4Stages + s;
+                    M4_TIMED(0, ptx::mbar_wait(bars + kEmpty + 8 * s, ph ^ 1u, p.error, kW4Producer));
+                    const uint32_t sbase = base + s * kM4StageBytes;
+                    const uint32_t fb = bars + kFull + 8 * s;
+                    if (ptx::elect_one_sync()) {
+                        ptx::mbar_arrive_expect_tx(fb, kM4StageBytes);
+#pragma unroll
+                        for (int t = 0; t < kM4Tiles; ++t)
+                            ptx::bulk_g2s_hint(sbase + t * kM4PkBytes,
+                                               mk + (size_t)t * kMaskTileBytes + (size_t)c * kM4PkBytes, kM4PkBytes, fb,
+                                               pol_stream);
+                        ptx::bulk_g2s_hint(sbase + kM4OffQ, p.qm + (size_t)c * kM4QBytes, kM4QBytes, fb, pol_keep);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp >= kM4IssuerWarp0 && warp < kExpWarp0) {
+    } else if (warp >= kM4IssuerWarp0 && warp < kP4ExpWarp0) {
         // ------------------------------------------------------------------ UMMA issuers
-        // warp (par, t) issues the stages g = par (mod kIss) of row tile t into its own accumulator
+        // warp (par, t) issues the stages of parity `par` of row tile t into its own accumulator
         const int t = (warp - kM4IssuerWarp0) % kM4Tiles;
         const int par = (warp - kM4IssuerWarp0) / kM4Tiles;
         const uint32_t sf = tmem_base + kM4SfCol;
-        const uint32_t my_pairs = pair0 < pair_end ? (pair_end - pair0 + pair_step - 1) / pair_step : 0;
-        const uint32_t total = my_pairs * kM4StagesPerTile;
-        int stage = par, aj = par, c = par;         // ring positions and stage-within-tile of g
-        uint32_t phase = 0, aphase = 0, it = 0, d = 0;
-        for (uint32_t g = par; g < total; g += kIss) {
-            if (c == par) {                          // first stage of a tile: the accumulator must have been drained
-                const uint32_t buf = kAccBufs == 2 ? (it & 1u) : 0u;
-                const uint32_t par_t = kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
-                M4_TIMED(2, ptx::mbar_wait(tempty_bar(buf, t), par_t ^ 1u, p.error, kW4MmaTmem));
-                ptx::tc_fence_after();
-                d = tmem_base + ((buf * kM4Tiles + t) * kIss + par) * 32u;
-            }
-            M4_TIMED(0, ptx::mbar_wait(full_bar(stage), phase, p.error, kW4MmaFull));
-            M4_TIMED(1, ptx::mbar_wait(afull_bar(aj, t), aphase, p.error, kW4MmaA));
-            const int ar = aj >= kM4ARing ? aj - kM4ARing : aj;
+        const uint32_t d = tmem_base + (t * 2 + par) * 32u;
+        // everything that depends on (par, t) folded into bases; the unrolled visit u adds immediates
+        const uint32_t full0 = bars + kFull + 8 * par, empty0 = bars + kEmpty + 8 * par;
+        const uint32_t afull0 = bars + kAFull + 8 * (2 * par + t), aempty0 = bars + kAEmpty + 8 * (2 * par + t);
+        const uint32_t q0 = base + par * kM4StageBytes + kM4OffQ;
+        const uint32_t a0 = tmem_base + kM4ACol + par * kM4ASlotCols + t * 32u;    // slot of j = par
+        const uint32_t tfull = bars + kTFull + 8 * t, tempty = bars + kTEmpty + 8 * t;
+        uint32_t ph = 0;
+        for (uint32_t it = 0; it < my_pairs; ++it) {
+            M4_TIMED(2, ptx::mbar_wait(tempty, (it & 1u) ^ 1u, p.error, kW4MmaTmem));    // accumulator drained
             ptx::tc_fence_after();
-            const uint32_t qbase = base + stage * kM4StageBytes + kM4OffQ;
-            const uint32_t abase = tmem_base + kM4ACol + ar * kM4ASlotCols + t * 32u;
-            const uint32_t blo0 = ((qbase & 0x3FFFFu) >> 4) | (1u << 16);
-            const bool last = c + kIss >= kM4StagesPerTile;
-            if (ptx::elect_one_sync()) {
+            for (int rev = 0; rev < kRevsPerTile; ++rev, ph ^= 1u) {
 #pragma unroll
-                for (int k = 0; k < ((kFlags & 4) ? 0 : 4); ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
-                    umma_mxf4_ts(d, abase + k * 8, blo0 + ((32 * k) >> 4), kM4DescHiSw128, kM4Idesc, sf,
-                                 k ? 1u : (c != par ? 1u : 0u));
-                ptx::umma_commit(aempty_bar(aj, t));
-                ptx::umma_commit(empty_bar(stage));
-                if (last) ptx::umma_commit(tfull_bar(kAccBufs == 2 ? (it & 1u) : 0u, t));
+                for (int u = 0; u < kP4Period; ++u) {            // stage / barrier index j = par + 2u
+                    M4_TIMED(0, ptx::mbar_wait(full0 + 16 * u, ph, p.error, kW4MmaFull));
+                    M4_TIMED(1, ptx::mbar_wait(afull0 + 32 * u, ph, p.error, kW4MmaA));
+                    ptx::tc_fence_after();
+                    const bool low = par ? (u < 2) : (u < 3);    // j = par + 2u < 5; slot j % 5
+                    const uint32_t abase = low ? a0 + 2 * u * kM4ASlotCols : a0 + (2 * u - kM4ARing) * kM4ASlotCols;
+                    const uint32_t blo0 = (((q0 + 2 * u * kM4StageBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                    if (ptx::elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < ((kFlags & 4) ? 0 : 4); ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
+                            umma_mxf4_ts(d, abase + k * 8, blo0 + ((32 * k) >> 4), kM4DescHiSw128, kM4Idesc, sf,
+                                         (k | u | rev) ? 1u : 0u);
+                        ptx::umma_commit(aempty0 + 32 * u);
+                        ptx::umma_commit(empty0 + 16 * u);
+                        if (rev == kRevsPerTile - 1 && u == kP4Period - 1) ptx::umma_commit(tfull);
+                    }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
-            stage += kIss;
-            if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
-            aj += kIss;
-            if (aj >= kABars) { aj -= kABars; aphase ^= 1u; }
-            c += kIss;
-            if (c >= kM4StagesPerTile) { c -= kM4StagesPerTile; ++it; }
         }
-    } else if (warp >= kExpWarp0) {
+    } else if (warp >= kP4ExpWarp0) {
         // ------------------------------------------------------------------ expanders: packed bits -> e2m1 A operand
-        const int set = (warp - kExpWarp0) / (4 * kM4Tiles);      // this warp expands the stages g = set (mod kSets)
-        const int t = ((warp - kExpWarp0) >> 2) % kM4Tiles;       // row tile of this warp
+        const int set = (warp - kP4ExpWarp0) / (4 * kM4Tiles);      // this warp expands the stages of parity `set`
+        const int t = ((warp - kP4ExpWarp0) >> 2) % kM4Tiles;       // row tile of this warp
         const int quad = warp & 3;                                  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const uint32_t my_pairs = pair0 < pair_end ? (pair_end - pair0 + pair_step - 1) / pair_step : 0;
-        const uint32_t total = my_pairs * kM4StagesPerTile;         // stages of this CTA, all pairs
-        int stage = set, aj = set;
-        uint32_t phase = 0, aphase = 0;
-        {
-            for (uint32_t g = set; g < total; g += kSets) {
-                // the slot was last used by stage g - kM4ARing: its commit went to barrier (aj + kM4ARing) % kABars
-                const int ar = aj >= kM4ARing ? aj - kM4ARing : aj;
-                const int jw = aj >= kM4ARing ? aj - kM4ARing : aj + kM4ARing;
-                const uint32_t wpar = aj >= kM4ARing ? aphase : aphase ^ 1u;
-                M4_TIMED(0, ptx::mbar_wait(full_bar(stage), phase, p.error, kW4ExpFull));
-                if (!(kFlags & 32)) {
-                    M4_TIMED(1, ptx::mbar_wait(aempty_bar(jw, t), wpar, p.error, kW4ExpA));
-                    ptx::tc_fence_after();
-                }
+        const uint32_t full0 = bars + kFull + 8 * set, empty0 = bars + kEmpty + 8 * set;
+        const uint32_t afull0 = bars + kAFull + 8 * (2 * set + t), aempty0 = bars + kAEmpty + 8 * (2 * set + t);
+        const uint8_t* pk0 = base_ptr + set * kM4StageBytes + t * kM4PkBytes + row * 16;
+        const uint32_t a0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kM4ACol + set * kM4ASlotCols + t * 32u;   // slot of j = set
+        uint32_t ph = 0;
+        for (uint32_t per = 0; per < my_pairs * kRevsPerTile; ++per, ph ^= 1u) {
+#pragma unroll
+            for (int u = 0; u < kP4Period; ++u) {                // stage / barrier index j = set + 2u, slot j % 5
+                M4_TIMED(0, ptx::mbar_wait(full0 + 16 * u, ph, p.error, kW4ExpFull));
                 uint32_t v[32];
                 if (!(kFlags & 2)) {
-                    const uint8_t* pk = base_ptr + stage * kM4StageBytes + t * kM4PkBytes;
-                    const uint4 x0 = *reinterpret_cast<const uint4*>(pk + row * 16);                       // bits 0..127
-                    const uint4 x1 = *reinterpret_cast<const uint4*>(pk + kMaskChunkBytes + row * 16);     // bits 128..255
+                    const uint8_t* pk = pk0 + 2 * u * kM4StageBytes;
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(pk);                       // bits 0..127
+                    const uint4 x1 = *reinterpret_cast<const uint4*>(pk + kMaskChunkBytes);     // bits 128..255
                     const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                     for (int w = 0; w < 8; ++w) {
@@ -273,30 +265,25 @@ __global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kern
                         v[4 * w + 2] = xs[w] & 0x44444444u;             // 2.0
                         v[4 * w + 3] = (xs[w] >> 1) & 0x44444444u;      // bit 3 of each nibble, moved off the sign: 2.0
                     }
-                }
-                if (kFlags & 32) {
                     // the expanded words are in registers: hand the packed bytes back, then wait for the TMEM slot
 #pragma unroll
                     for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));     // keep the logic ops above the wait
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(empty_bar(stage));
-                    M4_TIMED(1, ptx::mbar_wait(aempty_bar(jw, t), wpar, p.error, kW4ExpA));
-                    ptx::tc_fence_after();
                 }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(empty0 + 16 * u);
+                // j = set + 2u.  The slot j % 5 was last used by stage g - 5, whose commit went to barrier (j + 5) % 10:
+                // for j < 5 that use belongs to the previous revolution
+                const bool low = set ? (u < 2) : (u < 3);        // j < 5
+                M4_TIMED(1, ptx::mbar_wait(low ? aempty0 + 32 * u + 16 * kM4ARing : aempty0 + 32 * u - 16 * kM4ARing,
+                                           low ? ph ^ 1u : ph, p.error, kW4ExpA));
+                ptx::tc_fence_after();
                 if (!(kFlags & 2)) {
-                    tmem_st32_m4(tmem_base + lane_addr + kM4ACol + ar * kM4ASlotCols + t * 32u, v);
+                    tmem_st32_m4(low ? a0 + 2 * u * kM4ASlotCols : a0 + (2 * u - kM4ARing) * kM4ASlotCols, v);
                     M4_TIMED(2, asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"));
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    ptx::mbar_arrive(afull_bar(aj, t));
-                    if (!(kFlags & 32)) ptx::mbar_arrive(empty_bar(stage));   // this warp no longer needs the packed bytes
-                }
-                stage += kSets;
-                if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
-                aj += kSets;
-                if (aj >= kABars) { aj -= kABars; aphase ^= 1u; }
+                if (lane == 0) ptx::mbar_arrive(afull0 + 32 * u);
             }
         }
     } else {
@@ -304,36 +291,29 @@ __global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kern
         const int row = threadIdx.x;
         uint32_t it = 0;
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step, ++it) {
-            const uint32_t buf = kAccBufs == 2 ? (it & 1u) : 0u;
-            const uint32_t par_t = kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
 #pragma unroll 1
             for (int t = 0; t < kM4Tiles; ++t) {
-                M4_TIMED(0, ptx::mbar_wait(tfull_bar(buf, t), par_t, p.error, kW4Epilogue));
+                M4_TIMED(0, ptx::mbar_wait(bars + kTFull + 8 * t, it & 1u, p.error, kW4Epilogue));
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * kM4Tiles + t) * kIss * 32u;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + t * 64u;
                 const int64_t trow0 = ((int64_t)pair * kM4Tiles + t) * kTileRows;
                 int64_t lo = (int64_t)p.row_begin - trow0, hi = (int64_t)p.row_end - trow0;
                 const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
                 const int r1 = (int)(hi < 0 ? 0 : (hi > kTileRows ? kTileRows : hi));
                 const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
-                uint32_t a[32];
+                uint32_t a[32], b2[32];
                 ptx::tmem_ld32(taddr, a);
+                ptx::tmem_ld32(taddr + 32u, b2);            // the other issuing warp's partial sums
                 ptx::tmem_wait_ld();
-                if (kIss == 2) {                    // the other issuer's partial sums (f32, exact)
-                    uint32_t b2[32];
-                    ptx::tmem_ld32(taddr + 32u, b2);
-                    ptx::tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b2[j]));
-                }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(buf, t));
+                if (lane == 0) ptx::mbar_arrive(bars + kTEmpty + 8 * t);
                 const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(p.den_out) + tile_off) & 15);
                 uint8_t* st = out_stage_ptr + shift + row * kOutRowBytes;
 #pragma unroll
                 for (int j = 0; j < IRIS_ROTATIONS; ++j)
-                    *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)__float2uint_rn(__uint_as_float(a[j]));
+                    *reinterpret_cast<uint16_t*>(st + 2 * j) =
+                        (uint16_t)__float2uint_rn(__uint_as_float(a[j]) + __uint_as_float(b2[j]));
                 ptx::named_bar_sync(1, 128);
                 if (r1 > r0)
                     copy_out_rows(out_stage_ptr, reinterpret_cast<uint8_t*>(p.den_out) + tile_off - shift,
@@ -351,42 +331,37 @@ __global__ void __launch_bounds__(m4_threads(kSets, kIss), 1) mask_scan_fp4_kern
     if (warp == kM4IssuerWarp0) ptx::tmem_dealloc(tmem_base, kM4TmemCols);
 }
 
-template <int kSets, int kIss, int kFlags, int kStages>
+template <int kFlags>
 static cudaError_t launch_m4_t(const ScanParams& p, int num_sms, cudaStream_t stream) {
     static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(mask_scan_fp4_kernel<kSets, kIss, kFlags, kStages>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, m4_smem_bytes(kStages));
+        e = cudaFuncSetAttribute(mask_scan_fp4_kernel<kFlags>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP4SmemBytes);
         if (e != cudaSuccess) return e;
         if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     if (p.tile_end <= p.tile_begin) return cudaSuccess;
     const uint32_t pairs = (p.tile_end + kM4Tiles - 1) / kM4Tiles - p.tile_begin / kM4Tiles;
     const uint32_t grid = pairs < (uint32_t)num_sms ? pairs : (uint32_t)num_sms;
-    mask_scan_fp4_kernel<kSets, kIss, kFlags, kStages>
-        <<<grid, m4_threads(kSets, kIss), m4_smem_bytes(kStages), stream>>>(p);
+    mask_scan_fp4_kernel<kFlags><<<grid, kP4Threads, kP4SmemBytes, stream>>>(p);
     count_launch_external();
     return cudaGetLastError();
 }
 
 cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t stream) {
-    // IRIS_M4_VARIANT = "<sets><issuers per tile><flags, 3 digits>" selects an A/B variant (diagnostics).
+    // IRIS_M4_VARIANT selects a diagnostic variant (flags above); unset = the product kernel.
     static const int variant = [] {
         const char* e = getenv("IRIS_M4_VARIANT");
-        return e ? atoi(e) : 21000;
+        return e ? atoi(e) : 0;
     }();
     switch (variant) {
-        case 22000: return launch_m4_t<2, 2, 0, 12>(p, num_sms, stream);
-        case 22032: return launch_m4_t<2, 2, 32, 12>(p, num_sms, stream);
-        case 21032: return launch_m4_t<2, 1, 32, 12>(p, num_sms, stream);
-        case 22256: return launch_m4_t<2, 2, 256, 12>(p, num_sms, stream);
-        case 22288: return launch_m4_t<2, 2, 288, 12>(p, num_sms, stream);
-        case 22002: return launch_m4_t<2, 2, 2, 12>(p, num_sms, stream);
-        case 22004: return launch_m4_t<2, 2, 4, 12>(p, num_sms, stream);
-        default: return launch_m4_t<2, 1, 0, 12>(p, num_sms, stream);
+        case 2: return launch_m4_t<2>(p, num_sms, stream);
+        case 4: return launch_m4_t<4>(p, num_sms, stream);
+        case 6: return launch_m4_t<6>(p, num_sms, stream);
+        case 256: return launch_m4_t<256>(p, num_sms, stream);
+        default: return launch_m4_t<0>(p, num_sms, stream);
     }
 }
 
