@@ -246,18 +246,53 @@ def _time_ms(stream, fn, sync, warmup=2, iters=5, cool_s=0.0):
     return s.elapsed_time(e) / iters
 
 
+def hbm_peak_gbs():
+    """The roofline denominator: the driver's measured copy bandwidth, else the profiling recipe's fallback."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _steady_ms(stream, fn, sync, settle_s=0.3, iters=100):
+    """Mean device time of a sub-millisecond kernel in steady state: launch back to back for settle_s, then time
+    `iters` launches with CUDA events on the launch stream (SM clock sampled meanwhile, left in _NVML['last_mhz'])."""
+    t0 = time.time()
+    while time.time() - t0 < settle_s:
+        for _ in range(20):
+            fn()
+        sync()
+    return _time_ms(stream, fn, sync, warmup=0, iters=iters)
+
+
 def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     """BASELINE configs[2] (denominators only) and configs[3] (64 queries as a dense int8 GEMM) on the same shard,
     kernel-only, reported next to the headline so the driver's own run carries them."""
     import torch
 
     out = {}
-    # a 0.4 ms kernel: enough warm-up launches for the SM clock to come back up after the host-side gap before it
-    ms = _time_ms(stream, lambda: iris.match(None, me, db, 0, rows, None, d_den), db.synchronize, warmup=25, iters=25)
-    out["denominators_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
-                                   "algorithmic_GBps": rows * 1662 / (ms * 1e-3) / 1e9,
-                                   "sm_mhz": _NVML["last_mhz"],
-                                   "note": "bound by the per-instruction cost of N = 32 UMMAs, not by HBM (DESIGN.md 5.3)"}
+    # BASELINE configs[2]: denominators-only sweep, 100 k - 4 M masks (a masks-only shard; uniform bits, one query mask).
+    # These are 0.03 - 1.1 ms kernels: each size is timed over 100 launches after 0.3 s of back-to-back launches so the
+    # SM clock has settled (the kernel is within ~10 % of its HBM floor but still follows the SM clock).
+    peak = hbm_peak_gbs()[0]
+    sweep_rows = [n for n in (100_000, 250_000, 500_000, 1_000_000, 2_000_000, 4_000_000) if n <= 4 * rows]
+    mdb = iris.Database(max(sweep_rows), device=db.device, shares=False)
+    mdb.generate(SEED, 0, max(sweep_rows))
+    mdb.set_stream(stream.cuda_stream)
+    m_den = torch.empty((max(sweep_rows), 31), dtype=torch.int16, device="cuda")
+    sweep = []
+    for n in sweep_rows:
+        ms = _steady_ms(stream, lambda: iris.match(None, me, mdb, 0, n, None, m_den), mdb.synchronize)
+        sweep.append({"rows": n, "ms": ms, "comparisons_per_s": n / (ms * 1e-3),
+                      "algorithmic_GBps": n * 1662 / (ms * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": n * 1662 / (ms * 1e-3) / 1e9 / peak, "sm_mhz": _NVML["last_mhz"]})
+    mdb.close()
+    del m_den
+    one_m = next((x for x in sweep if x["rows"] == 1_000_000), sweep[-1])
+    out["denominators_only_1q"] = dict(one_m, note="4-bit tcgen05 operands expanded into tensor memory (DESIGN.md 5.3); "
+                                       "algorithmic bytes = 1 600 B read + 62 B written per row")
+    out["denominators_sweep"] = sweep
     ms = _time_ms(stream, lambda: iris.match(de, None, db, 0, rows, d_dist, None), db.synchronize, warmup=3, iters=10)
     out["distances_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
                                 "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9, "sm_mhz": _NVML["last_mhz"]}
@@ -557,12 +592,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        with open(peaks_path) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak_gbs()
     achieved = rows * BYTES_PER_ROW_FUSED / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_fused_traffic.json")

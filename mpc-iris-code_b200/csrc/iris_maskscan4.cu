@@ -1,10 +1,9 @@
 // Denominators-only scan with 4-BIT operands (BASELINE config 3): popcount(rot(qmask, j-15) & dbmask_i) for ONE query
 // mask over the resident masks, reference src/lib.rs:69-79 -> src/arch/generic.rs:4-9.
 //
-// Same organisation as iris_maskscan.cu (packed bits -> expander warps -> A operand in TENSOR MEMORY -> TS-form
-// UMMA), but the operands are e2m1 nibbles and the instruction is tcgen05.mma kind::mxf4 (block-scaled, K = 64):
-// an N = 32 UMMA costs ~30 cycles whatever it computes, so covering 64 mask bits per instruction
-// instead of 32 halves the tensor-side time, and the expanders store half the bytes with 5 instead of 8 logic
+// Packed bits -> expander warps -> A operand in TENSOR MEMORY -> TS-form UMMA, as in iris_maskscan.cu, but the
+// operands are e2m1 nibbles and the instruction is tcgen05.mma kind::mxf4 (block-scaled, K = 64): one instruction
+// covers 64 mask bits of 128 rows instead of 32, and the expanders store half the bytes with 5 instead of 8 logic
 // operations per 32 bits.
 //
 // Arithmetic (exact): a database bit becomes the nibble  x & (1 << t)  of its 32-bit word, i.e. e2m1 0.5, 1.0 or 2.0
@@ -17,11 +16,12 @@
 // 32 * w + 4 * j + t; prep_mask_query_fp4_kernel builds the query operand in the same order.
 //
 // Per stage: 256 mask bits of 2 x 128 rows = 2 x 4 KiB of packed database + 4 KiB of query operand.
-//   producer (warp 4)     : 3 bulk copies into a 12-deep smem ring
-//   expanders (warps 7-22): 2 x LDS.128 -> 40 logic ops -> 1 x tcgen05.st.32x32b.x32 into a 5-deep TMEM ring;
-//                           two sets of 8 warps alternate stages
-//   issuers (warps 5, 6)  : 4 x tcgen05.mma kind::mxf4 (A = TMEM, B = smem) per stage, one warp per tile
-//   epilogue (warps 0-3)  : tcgen05.ld, f32 -> u16, 62-byte rows; accumulators double-buffered
+//   producers (warps 4, 25): bulk copies of the packed masks (20-deep ring) and of the query operand (10-deep ring)
+//   expanders (warps 9-24) : 2 x LDS.128 -> 40 logic ops -> 1 x tcgen05.st.32x32b.x32 into a 5-deep TMEM ring;
+//                            two sets of 8 warps take the stages of one parity each
+//   issuers (warps 5-8)    : 4 x tcgen05.mma kind::mxf4 (A = TMEM, B = smem) per stage; two warps per tile, one per
+//                            stage parity, each with its own accumulator
+//   epilogue (warps 0-3)   : tcgen05.ld of both partial sums, f32 add -> u16, 62-byte rows
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -41,16 +41,11 @@ constexpr int kM4StageBits = 256;
 constexpr int kM4StagesPerTile = IRIS_BITS / kM4StageBits;        // 50
 constexpr int kM4PkBytes = kM4StageBits / 8 * kTileRows;          // 4 KiB of packed bits per tile and stage
 constexpr int kM4QBytes = kQm4StageBytes;                         // 4 KiB: 32 rotations x 256 nibbles
-constexpr int kM4OffQ = kM4Tiles * kM4PkBytes;
-constexpr int kM4StageBytes = kM4OffQ + kM4QBytes;                // 12 KiB
 constexpr int kM4ARing = 5;                                       // TMEM A slots of 2 tiles x 32 columns
 constexpr int kM4OutStageBytes = 8192;
 constexpr int kM4BarBytes = 1024;
-constexpr int m4_smem_bytes(int stages) { return 1024 + stages * kM4StageBytes + kM4OutStageBytes + kM4BarBytes; }
-constexpr int kM4IssuerWarp0 = 5;                                 // issuer warps: [k-parity][tile]
-constexpr int m4_exp_warp0(int iss) { return kM4IssuerWarp0 + iss * kM4Tiles; }   // expander warps: [set][tile][TMEM lane quadrant]
-constexpr int m4_threads(int sets, int iss) { return (m4_exp_warp0(iss) + sets * 4 * kM4Tiles) * 32; }   // 736 for 2 sets, 1 issuer per tile
-constexpr uint32_t kM4AccCols = 2 * kM4Tiles * 32;                // [buffer][tile] x 32 f32 columns
+constexpr int kM4IssuerWarp0 = 5;
+constexpr uint32_t kM4AccCols = 2 * kM4Tiles * 32;                // [tile][issuer] x 32 f32 columns
 constexpr uint32_t kM4SfCol = kM4AccCols;                         // 32 columns of 0x7F scale-factor bytes
 constexpr uint32_t kM4ACol = kM4SfCol + 32;
 constexpr uint32_t kM4ASlotCols = kM4Tiles * 32;                  // 64
@@ -58,7 +53,7 @@ constexpr uint32_t kM4TmemCols = 512;
 static_assert(IRIS_BITS % kM4StageBits == 0, "stages must tile the K dimension");
 static_assert(kM4StageBits == 2 * 8 * kMaskChunkBytes / kTileRows, "a stage is two 128-bit mask chunks");
 static_assert(kM4ACol + kM4ARing * kM4ASlotCols <= kM4TmemCols, "TMEM budget");
-static_assert(kM4StageBytes % 1024 == 0 && kM4OffQ % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+static_assert(kM4QBytes % 1024 == 0 && kM4PkBytes % 1024 == 0, "operand tiles must stay 1024-byte aligned");
 
 enum M4Watchdog { kW4Producer = 501, kW4MmaFull = 502, kW4MmaA = 503, kW4MmaTmem = 504, kW4ExpFull = 505, kW4ExpA = 506, kW4Epilogue = 507 };
 
@@ -90,7 +85,9 @@ constexpr uint32_t kM4Idesc = (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | (1u 
 constexpr uint32_t kM4DescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
 
 // ---------------------------------------------------------------------------------------------------------
-// Period-unrolled kernel (the product path).  Rings: 10 smem stages, 5 TMEM A slots with 10 barriers per direction
+// Period-unrolled kernel (the product path).  Rings: 20 packed-mask stages (dynamic index; released as soon as the
+// expanders hold the words in registers, so the ring only has to cover the HBM latency), 10 query-operand stages
+// (released by the UMMA commits), 5 TMEM A slots with 10 barriers per direction
 // (stage g uses slot g % 5 and barrier g % 10, so a barrier always pairs the same expander set with the same issuing
 // warp and nobody waits on a phase two uses ahead).  Two expander sets and two issuing warps per tile each take the
 // stages of one parity, so for every role the ring state repeats after 5 visits (= 10 stages = one revolution of
@@ -99,15 +96,21 @@ constexpr uint32_t kM4DescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 
 // TS-form N = 32 UMMA retires every 16 cycles when issued back to back), hence two of them per tile, each with its
 // own accumulator (the epilogue adds the two partial sums; f32, exact).
 // kFlags (diagnostics): 2 / 4 = timing only, no expansion / no UMMAs (wrong results); 256 = per-role wait profile.
-constexpr int kP4Stages = 10;
+constexpr int kP4Stages = 10;                                     // query-operand ring (4 KiB stages) = A-barrier ring
+constexpr int kP4DbStages = 20;                                   // packed-mask ring (2 x 4 KiB stages), covers the HBM latency
 constexpr int kP4ABars = 2 * kM4ARing;
 constexpr int kP4Period = 5;                                      // visits per role and revolution
 constexpr int kP4IssWarps = 2 * kM4Tiles;                         // [parity][tile]
 constexpr int kP4ExpWarp0 = kM4IssuerWarp0 + kP4IssWarps;         // 9: [set][tile][TMEM lane quadrant]
-constexpr int kP4Threads = (kP4ExpWarp0 + 2 * 4 * kM4Tiles) * 32; // 800
-constexpr int kP4SmemBytes = m4_smem_bytes(kP4Stages);
-static_assert(kP4Stages == kP4ABars && kP4Stages == 2 * kP4Period, "one revolution of both rings per period");
+constexpr int kP4QWarp = kP4ExpWarp0 + 2 * 4 * kM4Tiles;          // 25: query-operand producer
+constexpr int kP4Threads = (kP4QWarp + 1) * 32;                   // 832
+constexpr int kP4DbStageBytes = kM4Tiles * kM4PkBytes;            // 8 KiB
+constexpr int kP4DbBytes = kP4DbStages * kP4DbStageBytes;         // 160 KiB
+constexpr int kP4QRingBytes = kP4Stages * kM4QBytes;              // 40 KiB
+constexpr int kP4SmemBytes = 1024 + kP4DbBytes + kP4QRingBytes + kM4OutStageBytes + kM4BarBytes;
+static_assert(kP4Stages == kP4ABars && kP4Stages == 2 * kP4Period, "one revolution of the query and A rings per period");
 static_assert(kM4StagesPerTile % kP4Stages == 0, "a tile is a whole number of revolutions");
+static_assert(kP4DbStages % 2 == 0, "each packed-mask stage always belongs to the same expander set");
 static_assert(kP4SmemBytes <= 232448, "exceeds 227 KiB of shared memory");
 
 template <int kFlags>
@@ -116,11 +119,13 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* const base_ptr = smem_raw + (base - raw_addr);
-    uint8_t* const out_stage_ptr = base_ptr + kP4Stages * kM4StageBytes;
-    const uint32_t bars = base + kP4Stages * kM4StageBytes + kM4OutStageBytes;
-    // barrier table (8 bytes each): full[10] empty[10] afull[10][2] aempty[10][2] tfull[2] tempty[2]
-    constexpr uint32_t kFull = 0, kEmpty = 8 * kP4Stages, kAFull = 16 * kP4Stages, kAEmpty = kAFull + 16 * kP4ABars,
-                       kTFull = kAEmpty + 16 * kP4ABars, kTEmpty = kTFull + 16, kBarEnd = kTEmpty + 16;
+    const uint32_t qring = base + kP4DbBytes;
+    uint8_t* const out_stage_ptr = base_ptr + kP4DbBytes + kP4QRingBytes;
+    const uint32_t bars = base + kP4DbBytes + kP4QRingBytes + kM4OutStageBytes;
+    // barrier table (8 bytes each): full_db[20] empty_db[20] full_q[10] empty_q[10] afull[10][2] aempty[10][2] tfull[2] tempty[2]
+    constexpr uint32_t kFullDb = 0, kEmptyDb = 8 * kP4DbStages, kFullQ = 16 * kP4DbStages, kEmptyQ = kFullQ + 8 * kP4Stages,
+                       kAFull = kEmptyQ + 8 * kP4Stages, kAEmpty = kAFull + 16 * kP4ABars, kTFull = kAEmpty + 16 * kP4ABars,
+                       kTEmpty = kTFull + 16, kBarEnd = kTEmpty + 16;
     static_assert(kBarEnd + 8 <= kM4BarBytes, "barrier table");
     const uint32_t tmem_slot = bars + kBarEnd;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(out_stage_ptr + kM4OutStageBytes + kBarEnd);
@@ -129,9 +134,13 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        for (int s = 0; s < kP4DbStages; ++s) {
+            ptx::mbar_init(bars + kFullDb + 8 * s, 1);
+            ptx::mbar_init(bars + kEmptyDb + 8 * s, 4 * kM4Tiles);              // the expander warps of one set
+        }
         for (int s = 0; s < kP4Stages; ++s) {
-            ptx::mbar_init(bars + kFull + 8 * s, 1);
-            ptx::mbar_init(bars + kEmpty + 8 * s, 4 * kM4Tiles + kM4Tiles);     // expander warps + one commit per tile
+            ptx::mbar_init(bars + kFullQ + 8 * s, 1);
+            ptx::mbar_init(bars + kEmptyQ + 8 * s, kM4Tiles);                   // one commit per tile
         }
         for (int j = 0; j < kP4ABars * kM4Tiles; ++j) {
             ptx::mbar_init(bars + kAFull + 8 * j, 4);                            // 4 expander warps of one tile
@@ -172,27 +181,40 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     constexpr int kRevsPerTile = kM4StagesPerTile / kP4Stages;     // 5
 
     if (warp == 4) {
-        // ------------------------------------------------------------------ producer
+        // ------------------------------------------------------------------ packed-mask producer
         const uint64_t pol_stream = ptx::policy_evict_first();
-        const uint64_t pol_keep = ptx::policy_evict_last();
-        uint32_t ph = 0;
+        uint32_t sd = 0, dph = 0;
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
             const uint8_t* mk = p.masks + (size_t)pair * kM4Tiles * kMaskTileBytes;
+            for (int c = 0; c < kM4StagesPerTile; ++c) {
+                M4_TIMED(0, ptx::mbar_wait(bars + kEmptyDb + 8 * sd, dph ^ 1u, p.error, kW4Producer));
+                const uint32_t sbase = base + sd * kP4DbStageBytes;
+                const uint32_t fb = bars + kFullDb + 8 * sd;
+                if (ptx::elect_one_sync()) {
+                    ptx::mbar_arrive_expect_tx(fb, kP4DbStageBytes);
+#pragma unroll
+                    for (int t = 0; t < kM4Tiles; ++t)
+                        ptx::bulk_g2s_hint(sbase + t * kM4PkBytes, mk + (size_t)t * kMaskTileBytes + (size_t)c * kM4PkBytes,
+                                           kM4PkBytes, fb, pol_stream);
+                }
+                __syncwarp();
+                if (++sd == kP4DbStages) { sd = 0; dph ^= 1u; }
+            }
+        }
+    } else if (warp == kP4QWarp) {
+        // ------------------------------------------------------------------ query-operand producer (L2 resident image)
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        uint32_t ph = 0;
+        for (uint32_t it = 0; it < my_pairs; ++it) {
             for (int rev = 0; rev < kRevsPerTile; ++rev, ph ^= 1u) {
 #pragma unroll
                 for (int s = 0; s < kP4Stages; ++s) {
-                    const int c = rev * kP4Stages + s;
-                    M4_TIMED(0, ptx::mbar_wait(bars + kEmpty + 8 * s, ph ^ 1u, p.error, kW4Producer));
-                    const uint32_t sbase = base + s * kM4StageBytes;
-                    const uint32_t fb = bars + kFull + 8 * s;
+                    M4_TIMED(0, ptx::mbar_wait(bars + kEmptyQ + 8 * s, ph ^ 1u, p.error, kW4Producer));
+                    const uint32_t fb = bars + kFullQ + 8 * s;
                     if (ptx::elect_one_sync()) {
-                        ptx::mbar_arrive_expect_tx(fb, kM4StageBytes);
-#pragma unroll
-                        for (int t = 0; t < kM4Tiles; ++t)
-                            ptx::bulk_g2s_hint(sbase + t * kM4PkBytes,
-                                               mk + (size_t)t * kMaskTileBytes + (size_t)c * kM4PkBytes, kM4PkBytes, fb,
-                                               pol_stream);
-                        ptx::bulk_g2s_hint(sbase + kM4OffQ, p.qm + (size_t)c * kM4QBytes, kM4QBytes, fb, pol_keep);
+                        ptx::mbar_arrive_expect_tx(fb, kM4QBytes);
+                        ptx::bulk_g2s_hint(qring + s * kM4QBytes, p.qm + (size_t)(rev * kP4Stages + s) * kM4QBytes, kM4QBytes,
+                                           fb, pol_keep);
                     }
                     __syncwarp();
                 }
@@ -206,9 +228,9 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
         const uint32_t sf = tmem_base + kM4SfCol;
         const uint32_t d = tmem_base + (t * 2 + par) * 32u;
         // everything that depends on (par, t) folded into bases; the unrolled visit u adds immediates
-        const uint32_t full0 = bars + kFull + 8 * par, empty0 = bars + kEmpty + 8 * par;
+        const uint32_t full0 = bars + kFullQ + 8 * par, empty0 = bars + kEmptyQ + 8 * par;
         const uint32_t afull0 = bars + kAFull + 8 * (2 * par + t), aempty0 = bars + kAEmpty + 8 * (2 * par + t);
-        const uint32_t q0 = base + par * kM4StageBytes + kM4OffQ;
+        const uint32_t q0 = qring + par * kM4QBytes;
         const uint32_t a0 = tmem_base + kM4ACol + par * kM4ASlotCols + t * 32u;    // slot of j = par
         const uint32_t tfull = bars + kTFull + 8 * t, tempty = bars + kTEmpty + 8 * t;
         uint32_t ph = 0;
@@ -223,7 +245,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
                     ptx::tc_fence_after();
                     const bool low = par ? (u < 2) : (u < 3);    // j = par + 2u < 5; slot j % 5
                     const uint32_t abase = low ? a0 + 2 * u * kM4ASlotCols : a0 + (2 * u - kM4ARing) * kM4ASlotCols;
-                    const uint32_t blo0 = (((q0 + 2 * u * kM4StageBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                    const uint32_t blo0 = (((q0 + 2 * u * kM4QBytes) & 0x3FFFFu) >> 4) | (1u << 16);
                     if (ptx::elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < ((kFlags & 4) ? 0 : 4); ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
@@ -237,24 +259,24 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
                 }
             }
         }
-    } else if (warp >= kP4ExpWarp0) {
+    } else if (warp >= kP4ExpWarp0 && warp < kP4QWarp) {
         // ------------------------------------------------------------------ expanders: packed bits -> e2m1 A operand
         const int set = (warp - kP4ExpWarp0) / (4 * kM4Tiles);      // this warp expands the stages of parity `set`
         const int t = ((warp - kP4ExpWarp0) >> 2) % kM4Tiles;       // row tile of this warp
         const int quad = warp & 3;                                  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
-        const uint32_t full0 = bars + kFull + 8 * set, empty0 = bars + kEmpty + 8 * set;
         const uint32_t afull0 = bars + kAFull + 8 * (2 * set + t), aempty0 = bars + kAEmpty + 8 * (2 * set + t);
-        const uint8_t* pk0 = base_ptr + set * kM4StageBytes + t * kM4PkBytes + row * 16;
+        const uint8_t* pk0 = base_ptr + t * kM4PkBytes + row * 16;
         const uint32_t a0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kM4ACol + set * kM4ASlotCols + t * 32u;   // slot of j = set
-        uint32_t ph = 0;
+        uint32_t ph = 0, sd = set, dph = 0;                      // sd: position in the packed-mask ring (dynamic)
         for (uint32_t per = 0; per < my_pairs * kRevsPerTile; ++per, ph ^= 1u) {
 #pragma unroll
             for (int u = 0; u < kP4Period; ++u) {                // stage / barrier index j = set + 2u, slot j % 5
-                M4_TIMED(0, ptx::mbar_wait(full0 + 16 * u, ph, p.error, kW4ExpFull));
+                M4_TIMED(0, ptx::mbar_wait(bars + kFullDb + 8 * sd, dph, p.error, kW4ExpFull));
+                const uint32_t empty_db = bars + kEmptyDb + 8 * sd;
                 uint32_t v[32];
                 if (!(kFlags & 2)) {
-                    const uint8_t* pk = pk0 + 2 * u * kM4StageBytes;
+                    const uint8_t* pk = pk0 + sd * kP4DbStageBytes;
                     const uint4 x0 = *reinterpret_cast<const uint4*>(pk);                       // bits 0..127
                     const uint4 x1 = *reinterpret_cast<const uint4*>(pk + kMaskChunkBytes);     // bits 128..255
                     const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -270,7 +292,9 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
                     for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));     // keep the logic ops above the wait
                 }
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(empty0 + 16 * u);
+                if (lane == 0) ptx::mbar_arrive(empty_db);
+                sd += 2;
+                if (sd >= kP4DbStages) { sd -= kP4DbStages; dph ^= 1u; }
                 // j = set + 2u.  The slot j % 5 was last used by stage g - 5, whose commit went to barrier (j + 5) % 10:
                 // for j < 5 that use belongs to the previous revolution
                 const bool low = set ? (u < 2) : (u < 3);        // j < 5
