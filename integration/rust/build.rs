@@ -22,7 +22,7 @@ fn main() -> shadow_rs::SdResult<()> {
                 "-o",
                 &lib,
             ])
-            .args(["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu"].map(|f| format!("{src}/{f}")))
+            .args(["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan.cu", "iris_maskscan4.cu"].map(|f| format!("{src}/{f}")))
             .status()
             .expect("nvcc not found");
         assert!(status.success(), "nvcc failed");
