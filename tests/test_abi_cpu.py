@@ -48,6 +48,25 @@ def test_sass_contains_tcgen05_and_bulk_copy():
     sass = subprocess.run([cuobjdump, "-sass", iris.library_path()], capture_output=True, text=True).stdout
     for mnemonic in ("UTCIMMA", "LDTM", "UBLKCP"):
         assert mnemonic in sass, mnemonic
+    # the denominators-only scan: block-scaled 4-bit UMMA (tcgen05.mma kind::mxf4) fed from tensor memory (tcgen05.st)
+    for mnemonic in ("UTCOMMA", "STTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_diagnostic_cuda_sources_compile(tmp_path):
+    """tests/diagnostics/*.cu are the micro-benchmarks DESIGN.md quotes; keep them building for sm_100a."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    diag = os.path.join(ROOT, "tests", "diagnostics")
+    for src in ("umma_bench.cu", "sttm_bench.cu"):
+        out = tmp_path / (src + ".cubin")
+        subprocess.run([nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", "-o", str(out),
+                        os.path.join(diag, src)], check=True, capture_output=True)
+        assert out.stat().st_size > 0
 
 
 def test_no_cpu_fallback_without_a_gpu():
