@@ -883,6 +883,9 @@ extern "C" int iris_denominators(int device, const uint64_t* query, const uint64
 }
 
 // ------------------------------------------------------------------------------------ batched queries (dense GEMM)
+constexpr uint32_t kBatchDistanceGroup = 8;     // queries per accumulator tile of batch_distances_kernel
+constexpr uint32_t kBatchMaskGroup = 16;        // query masks per accumulator tile of batch_denominators_kernel
+constexpr uint32_t kBatchMaskTailLoop = 10;     // left-over masks handled by the single-query scan instead
 extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engines, uint32_t num_queries, iris_db* db,
                                              uint64_t row_begin, uint64_t row_end, uint16_t* out) {
     if (!engines || !db) return fail(IRIS_ERR_INVALID, "NULL argument");
@@ -905,10 +908,20 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
     auto body = [&]() -> int {
         for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxBatchQueries) {
             const uint32_t nq = std::min<uint32_t>(kMaxBatchQueries, num_queries - q0);
+            // A group of 8 queries costs one pass of the int8 GEMM (~4.5 ms per 1 M rows) however few of its slots
+            // are used; a single left-over query is cheaper on the HBM-bound single-query scan (~3.6 ms).
+            if (nq % kBatchDistanceGroup == 1) {
+                iris_distance_engine* e = engines[q0 + nq - 1];
+                int rc1 = scan_core(db, e->d_qd, nullptr, row_begin, row_end,
+                                    d_out + (size_t)(q0 + nq - 1) * rows * IRIS_ROTATIONS, nullptr, nullptr, e->fits_s8);
+                if (rc1) return rc1;
+                if (nq == 1) continue;
+            }
+            const uint32_t nb = nq % kBatchDistanceGroup == 1 ? nq - 1 : nq;
             BatchParams p{};
             p.shares = db->d_shares;
             bool all_s8 = true;
-            for (uint32_t i = 0; i < nq; ++i) {
+            for (uint32_t i = 0; i < nb; ++i) {
                 p.qd[i] = engines[q0 + i]->d_qd;
                 all_s8 &= engines[q0 + i]->fits_s8;
             }
@@ -917,7 +930,7 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
             p.row_end = row_end;
             p.pair_begin = (uint32_t)(row_begin / (2 * kTileRows));
             p.pair_end = (uint32_t)((row_end + 2 * kTileRows - 1) / (2 * kTileRows));
-            p.num_queries = nq;
+            p.num_queries = nb;
             p.error = db->d_error;
             CK(launch_batch_distances(p, all_s8, db->num_sms, db->stream));
         }
@@ -955,18 +968,57 @@ extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engine
     uint16_t* d_out = out;
     const size_t out_bytes = (size_t)num_queries * rows * kOutRowBytes;
     if (!out_dev) CK(cudaMalloc(&d_out, out_bytes + 64));
+    // Default: four query masks per pass of the 4-bit TMEM-operand scan (mask_scan_fp4_multi_kernel), left-over masks
+    // one by one on the single-query scan.  IRIS_BATCHDEN=i8 selects the int8 GEMM kernel (A/B measurements).
+    static const bool use_i8_gemm = [] {
+        const char* e = getenv("IRIS_BATCHDEN");
+        return e && e[0] == 'i';
+    }();
     auto body = [&]() -> int {
+        if (!use_i8_gemm) {
+            uint32_t q = 0;
+            for (; q + kMaskMultiQueries <= num_queries; q += kMaskMultiQueries) {
+                MultiMaskScanParams p{};
+                p.masks = db->d_masks;
+                for (int i = 0; i < kMaskMultiQueries; ++i) {
+                    p.qm4[i] = engines[q + i]->d_qm + kQmBytes;      // every mask operand buffer is [int8 image | 4-bit image]
+                    p.out[i] = d_out + (size_t)(q + i) * rows * IRIS_ROTATIONS;
+                }
+                p.row_begin = row_begin;
+                p.row_end = row_end;
+                p.tile_begin = (uint32_t)(row_begin / kTileRows);
+                p.tile_end = (uint32_t)((row_end + kTileRows - 1) / kTileRows);
+                p.error = db->d_error;
+                CK(launch_mask_scan_fp4_multi(p, db->num_sms, db->stream));
+            }
+            for (; q < num_queries; ++q) {
+                int rc1 = scan_core(db, nullptr, engines[q]->d_qm, row_begin, row_end, nullptr,
+                                    d_out + (size_t)q * rows * IRIS_ROTATIONS, nullptr);
+                if (rc1) return rc1;
+            }
+        } else
         for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxBatchQueries) {
             const uint32_t nq = std::min<uint32_t>(kMaxBatchQueries, num_queries - q0);
+            // A group of 16 query masks costs one pass of the int8 GEMM (~3.2 ms per 1 M rows) however few of its
+            // slots are used; up to kBatchMaskTailLoop left-over masks are cheaper one by one on the 4-bit
+            // single-query scan (~0.28 ms each).
+            const uint32_t tail = nq % kBatchMaskGroup;
+            const uint32_t nb = tail <= kBatchMaskTailLoop ? nq - tail : nq;
+            for (uint32_t i = nb; i < nq; ++i) {
+                int rc1 = scan_core(db, nullptr, engines[q0 + i]->d_qm, row_begin, row_end, nullptr,
+                                    d_out + (size_t)(q0 + i) * rows * IRIS_ROTATIONS, nullptr);
+                if (rc1) return rc1;
+            }
+            if (nb == 0) continue;
             BatchMaskParams p{};
             p.masks = db->d_masks;
-            for (uint32_t i = 0; i < nq; ++i) p.qm[i] = engines[q0 + i]->d_qm;
+            for (uint32_t i = 0; i < nb; ++i) p.qm[i] = engines[q0 + i]->d_qm;
             p.out = d_out + (size_t)q0 * rows * IRIS_ROTATIONS;
             p.row_begin = row_begin;
             p.row_end = row_end;
             p.pair_begin = (uint32_t)(row_begin / (2 * kTileRows));
             p.pair_end = (uint32_t)((row_end + 2 * kTileRows - 1) / (2 * kTileRows));
-            p.num_queries = nq;
+            p.num_queries = nb;
             p.error = db->d_error;
             CK(launch_batch_denominators(p, db->num_sms, db->stream));
         }

@@ -31,6 +31,18 @@ cudaError_t launch_mask_scan(const ScanParams& p, int num_sms, cudaStream_t stre
 // The same scan with e2m1 operands (kind::mxf4, iris_maskscan4.cu); p.qm must be the 4-bit image.
 cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_prep_mask_query_fp4(const uint8_t* d_qmask, uint8_t* d_qm4, cudaStream_t stream);
+// Four query masks per pass over the same expanded database operand (N = 128 UMMAs; iris_maskscan4.cu): the batched
+// denominators path.  qm4[i] are 4-bit operand images, out[i] = [row_end-row_begin][31] u16 each.
+constexpr int kMaskMultiQueries = 4;
+struct MultiMaskScanParams {
+    const uint8_t* masks;
+    const uint8_t* qm4[kMaskMultiQueries];
+    uint16_t* out[kMaskMultiQueries];
+    uint64_t row_begin, row_end;
+    uint32_t tile_begin, tile_end;
+    int* error;
+};
+cudaError_t launch_mask_scan_fp4_multi(const MultiMaskScanParams& p, int num_sms, cudaStream_t stream);
 
 // Query preparation (K3): reference DistanceEngine::new / MasksEngine::new (src/lib.rs:33-40, 60-67).
 cudaError_t launch_encode(const uint8_t* d_pattern, const uint8_t* d_mask, uint16_t* d_out, cudaStream_t stream);

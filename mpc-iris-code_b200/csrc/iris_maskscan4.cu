@@ -389,6 +389,258 @@ cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Four query masks per pass (the batched denominators path): the same packed bits -> TMEM A operand pipeline, but every
+// UMMA multiplies the expanded tile by the operand tiles of FOUR queries at once (N = 128, 64 cycles per instruction),
+// so the expansion, the HBM stream and the barrier traffic are shared by four queries and the kernel is bound by the
+// 4-bit tensor pipe (2 tiles x 4 K-steps x 64 cycles = 512 cycles per 256-bit stage).  TMEM: 2 x 128 accumulator
+// columns (single-buffered), 32 scale columns, a 3-slot A ring; one issuing warp per tile is enough at this N, and
+// the ring indices are dynamic (nothing here is issue-bound).
+constexpr int kMqN = 32 * kMaskMultiQueries;                                // 128 accumulator columns per tile
+constexpr int kMqARing = 3;
+constexpr int kMqABars = 2 * kMqARing;
+constexpr int kMqStages = 8;
+constexpr int kMqOffQ = kM4Tiles * kM4PkBytes;                              // 8 KiB of packed masks, then the query tiles
+constexpr int kMqStageBytes = kMqOffQ + kMaskMultiQueries * kM4QBytes;      // 24 KiB
+constexpr int kMqSmemBytes = 1024 + kMqStages * kMqStageBytes + kM4OutStageBytes + kM4BarBytes;
+constexpr int kMqExpWarp0 = kM4IssuerWarp0 + kM4Tiles;                      // 7: [set][tile][TMEM lane quadrant]
+constexpr int kMqThreads = (kMqExpWarp0 + 2 * 4 * kM4Tiles) * 32;           // 736
+constexpr uint32_t kMqSfCol = kM4Tiles * kMqN;                              // 256
+constexpr uint32_t kMqACol = kMqSfCol + 32;                                 // 288
+constexpr uint32_t kMqIdesc = (1u << 7) | (1u << 10) | ((uint32_t)(kMqN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+static_assert(kMqACol + kMqARing * kM4ASlotCols <= kM4TmemCols, "TMEM budget");
+static_assert(kMqSmemBytes <= 232448, "exceeds 227 KiB of shared memory");
+static_assert(kMqStageBytes % 1024 == 0 && kMqOffQ % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+static_assert(kMqStages % 2 == 0 && kMqABars % 2 == 0, "each ring position always belongs to the same expander set");
+
+enum MqWatchdog { kWqProducer = 521, kWqMmaFull = 522, kWqMmaA = 523, kWqMmaTmem = 524, kWqExpFull = 525, kWqExpA = 526, kWqEpilogue = 527 };
+
+__global__ void __launch_bounds__(kMqThreads, 1) mask_scan_fp4_multi_kernel(const MultiMaskScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* const base_ptr = smem_raw + (base - raw_addr);
+    uint8_t* const out_stage_ptr = base_ptr + kMqStages * kMqStageBytes;
+    const uint32_t bars = base + kMqStages * kMqStageBytes + kM4OutStageBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };                                       // stage landed (tx)
+    auto empty_bar = [&](int s) { return bars + 8u * (kMqStages + s); };                        // 8 expander warps + 2 commits
+    auto afull_bar = [&](int j, int t) { return bars + 8u * (2 * kMqStages + 2 * j + t); };     // 4 expander warps of tile t
+    auto aempty_bar = [&](int j, int t) { return bars + 8u * (2 * kMqStages + 2 * kMqABars + 2 * j + t); };   // one commit
+    auto tfull_bar = [&](int t) { return bars + 8u * (2 * kMqStages + 4 * kMqABars + t); };
+    auto tempty_bar = [&](int t) { return bars + 8u * (2 * kMqStages + 4 * kMqABars + 2 + t); };
+    constexpr int kNumBars = 2 * kMqStages + 4 * kMqABars + 4;
+    static_assert(8 * (kNumBars + 1) <= kM4BarBytes, "barrier table");
+    const uint32_t tmem_slot = bars + 8u * kNumBars;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(out_stage_ptr + kM4OutStageBytes + 8 * kNumBars);
+
+    const int warp = ptx::warp_idx_sync();      // warp-uniform role index
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMqStages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 4 * kM4Tiles + kM4Tiles);
+        }
+        for (int j = 0; j < kMqABars; ++j)
+            for (int t = 0; t < kM4Tiles; ++t) {
+                ptx::mbar_init(afull_bar(j, t), 4);
+                ptx::mbar_init(aempty_bar(j, t), 1);
+            }
+        for (int t = 0; t < kM4Tiles; ++t) {
+            ptx::mbar_init(tfull_bar(t), 1);
+            ptx::mbar_init(tempty_bar(t), 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == kM4IssuerWarp0) ptx::tmem_alloc(tmem_slot, kM4TmemCols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    if (warp < 4) {                             // scale factors: 1.0 everywhere (each warp fills its lane quadrant)
+        uint32_t ones[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ones[i] = 0x7F7F7F7Fu;
+        tmem_st32_m4(tmem_base + ((uint32_t)(warp * 32) << 16) + kMqSfCol, ones);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+
+    const uint32_t pair_begin = p.tile_begin / kM4Tiles;
+    const uint32_t pair_end = (p.tile_end + kM4Tiles - 1) / kM4Tiles;
+    const uint32_t pair0 = pair_begin + blockIdx.x;
+    const uint32_t pair_step = gridDim.x;
+    const uint32_t my_pairs = pair0 < pair_end ? (pair_end - pair0 + pair_step - 1) / pair_step : 0;
+    const uint32_t total = my_pairs * kM4StagesPerTile;         // stages of this CTA, all pairs
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ producer
+        const uint64_t pol_stream = ptx::policy_evict_first();
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
+            const uint8_t* mk = p.masks + (size_t)pair * kM4Tiles * kMaskTileBytes;
+            for (int c = 0; c < kM4StagesPerTile; ++c) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.error, kWqProducer);
+                const uint32_t sbase = base + stage * kMqStageBytes;
+                const uint32_t fb = full_bar(stage);
+                if (ptx::elect_one_sync()) {
+                    ptx::mbar_arrive_expect_tx(fb, kMqStageBytes);
+#pragma unroll
+                    for (int t = 0; t < kM4Tiles; ++t)
+                        ptx::bulk_g2s_hint(sbase + t * kM4PkBytes, mk + (size_t)t * kMaskTileBytes + (size_t)c * kM4PkBytes,
+                                           kM4PkBytes, fb, pol_stream);
+#pragma unroll
+                    for (int q = 0; q < kMaskMultiQueries; ++q)
+                        ptx::bulk_g2s_hint(sbase + kMqOffQ + q * kM4QBytes, p.qm4[q] + (size_t)c * kM4QBytes, kM4QBytes, fb,
+                                           pol_keep);
+                }
+                __syncwarp();
+                if (++stage == kMqStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= kM4IssuerWarp0 && warp < kMqExpWarp0) {
+        // ------------------------------------------------------------------ UMMA issuers: one warp per row tile
+        const int t = warp - kM4IssuerWarp0;
+        const uint32_t sf = tmem_base + kMqSfCol;
+        const uint32_t d = tmem_base + t * kMqN;
+        int stage = 0, aj = 0, c = 0;
+        uint32_t phase = 0, aphase = 0, it = 0;
+        for (uint32_t g = 0; g < total; ++g) {
+            if (c == 0) {                            // first stage of a tile: the accumulator must have been drained
+                ptx::mbar_wait(tempty_bar(t), (it & 1u) ^ 1u, p.error, kWqMmaTmem);
+                ptx::tc_fence_after();
+            }
+            ptx::mbar_wait(full_bar(stage), phase, p.error, kWqMmaFull);
+            ptx::mbar_wait(afull_bar(aj, t), aphase, p.error, kWqMmaA);
+            ptx::tc_fence_after();
+            const int ar = aj >= kMqARing ? aj - kMqARing : aj;
+            const uint32_t qbase = base + stage * kMqStageBytes + kMqOffQ;     // 4 x [32 rotations][128 B] = 128 B rows
+            const uint32_t abase = tmem_base + kMqACol + ar * kM4ASlotCols + t * 32u;
+            const uint32_t blo0 = ((qbase & 0x3FFFFu) >> 4) | (1u << 16);
+            if (ptx::elect_one_sync()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
+                    umma_mxf4_ts(d, abase + k * 8, blo0 + ((32 * k) >> 4), kM4DescHiSw128, kMqIdesc, sf, (k | c) ? 1u : 0u);
+                ptx::umma_commit(aempty_bar(aj, t));
+                ptx::umma_commit(empty_bar(stage));
+                if (c == kM4StagesPerTile - 1) ptx::umma_commit(tfull_bar(t));
+            }
+            __syncwarp();
+            if (++stage == kMqStages) { stage = 0; phase ^= 1u; }
+            if (++aj == kMqABars) { aj = 0; aphase ^= 1u; }
+            if (++c == kM4StagesPerTile) { c = 0; ++it; }
+        }
+    } else if (warp >= kMqExpWarp0) {
+        // ------------------------------------------------------------------ expanders: packed bits -> e2m1 A operand
+        const int set = (warp - kMqExpWarp0) / (4 * kM4Tiles);      // this warp expands the stages of parity `set`
+        const int t = ((warp - kMqExpWarp0) >> 2) % kM4Tiles;       // row tile of this warp
+        const int quad = warp & 3;                                  // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        int stage = set, aj = set;
+        uint32_t phase = 0, aphase = 0;
+        for (uint32_t g = set; g < total; g += 2) {
+            // slot aj % R was last used by stage g - R, whose commit went to barrier (aj + R) % 2R
+            const int ar = aj >= kMqARing ? aj - kMqARing : aj;
+            const int jw = aj >= kMqARing ? aj - kMqARing : aj + kMqARing;
+            const uint32_t wpar = aj >= kMqARing ? aphase : aphase ^ 1u;
+            ptx::mbar_wait(full_bar(stage), phase, p.error, kWqExpFull);
+            const uint8_t* pk = base_ptr + stage * kMqStageBytes + t * kM4PkBytes;
+            const uint4 x0 = *reinterpret_cast<const uint4*>(pk + row * 16);                       // bits 0..127
+            const uint4 x1 = *reinterpret_cast<const uint4*>(pk + kMaskChunkBytes + row * 16);     // bits 128..255
+            const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            uint32_t v[32];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                v[4 * w + 0] = xs[w] & 0x11111111u;             // 0.5
+                v[4 * w + 1] = xs[w] & 0x22222222u;             // 1.0
+                v[4 * w + 2] = xs[w] & 0x44444444u;             // 2.0
+                v[4 * w + 3] = (xs[w] >> 1) & 0x44444444u;      // bit 3 of each nibble, moved off the sign: 2.0
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));     // keep the logic ops above the wait
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty_bar(stage));              // the packed bytes are in registers
+            ptx::mbar_wait(aempty_bar(jw, t), wpar, p.error, kWqExpA);
+            ptx::tc_fence_after();
+            tmem_st32_m4(tmem_base + lane_addr + kMqACol + ar * kM4ASlotCols + t * 32u, v);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(afull_bar(aj, t));
+            stage += 2;
+            if (stage >= kMqStages) { stage -= kMqStages; phase ^= 1u; }
+            aj += 2;
+            if (aj >= kMqABars) { aj -= kMqABars; aphase ^= 1u; }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 0..3)
+        const int row = threadIdx.x;
+        uint32_t it = 0;
+        for (uint32_t pair = pair0; pair < pair_end; pair += pair_step, ++it) {
+#pragma unroll 1
+            for (int t = 0; t < kM4Tiles; ++t) {
+                ptx::mbar_wait(tfull_bar(t), it & 1u, p.error, kWqEpilogue);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + t * kMqN;
+                const int64_t trow0 = ((int64_t)pair * kM4Tiles + t) * kTileRows;
+                int64_t lo = (int64_t)p.row_begin - trow0, hi = (int64_t)p.row_end - trow0;
+                const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
+                const int r1 = (int)(hi < 0 ? 0 : (hi > kTileRows ? kTileRows : hi));
+                const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
+#pragma unroll
+                for (int q = 0; q < kMaskMultiQueries; ++q) {
+                    uint32_t a[32];
+                    ptx::tmem_ld32(taddr + 32 * q, a);
+                    ptx::tmem_wait_ld();
+                    if (q == kMaskMultiQueries - 1) {           // the accumulator is in registers: let the next tile start
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(tempty_bar(t));
+                    }
+                    uint8_t* outq = reinterpret_cast<uint8_t*>(p.out[q]);
+                    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(outq) + tile_off) & 15);
+                    uint8_t* st = out_stage_ptr + shift + row * kOutRowBytes;
+#pragma unroll
+                    for (int j = 0; j < IRIS_ROTATIONS; ++j)
+                        *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)__float2uint_rn(__uint_as_float(a[j]));
+                    ptx::named_bar_sync(1, 128);
+                    if (r1 > r0)
+                        copy_out_rows(out_stage_ptr, outq + tile_off - shift, (int)shift + r0 * kOutRowBytes,
+                                      (int)shift + r1 * kOutRowBytes, row);
+                    ptx::named_bar_sync(1, 128);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == kM4IssuerWarp0) ptx::tmem_dealloc(tmem_base, kM4TmemCols);
+}
+
+cudaError_t launch_mask_scan_fp4_multi(const MultiMaskScanParams& p, int num_sms, cudaStream_t stream) {
+    static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(mask_scan_fp4_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMqSmemBytes);
+        if (e != cudaSuccess) return e;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
+    }
+    if (p.tile_end <= p.tile_begin) return cudaSuccess;
+    const uint32_t pairs = (p.tile_end + kM4Tiles - 1) / kM4Tiles - p.tile_begin / kM4Tiles;
+    const uint32_t grid = pairs < (uint32_t)num_sms ? pairs : (uint32_t)num_sms;
+    mask_scan_fp4_multi_kernel<<<grid, kMqThreads, kMqSmemBytes, stream>>>(p);
+    count_launch_external();
+    return cudaGetLastError();
+}
+
 // Query operand image for mask_scan_fp4_kernel: [stage s < 50][rotation slot r < 32][128 B, SWIZZLE_128B]; the 16-byte
 // chunk `ch` of a row holds the output words 4 * ch + t (t = 0..3) of input word ch; nibble j of word t stands for
 // the bit 256 * s + 32 * ch + 4 * j + t of rot(qmask, r - 15) and holds 2.0, 1.0, 0.5, 0.5 (e2m1) for t = 0..3.

@@ -145,3 +145,88 @@ def test_kernel_variants_agree(iris):
         assert res.returncode == 0, res.stderr[-2000:]
         digests[mode] = res.stdout.strip().splitlines()[-1]
     assert digests["f"] == digests["i8"] == digests["smem"], digests
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# batched denominators: four query masks per pass of the 4-bit scan (mask_scan_fp4_multi_kernel), left-overs on the
+# single-query kernel
+
+
+@pytest.mark.parametrize("nq,rb,re", [(4, 0, 1500), (5, 1, 1499), (7, 255, 257), (8, 300, 1301), (3, 0, 1), (12, 1280, 1500)])
+def test_four_query_kernel_ragged_ranges(iris, shard, nq, rb, re):
+    db, masks = shard
+    qms = [O.gen_mask_rows(80 + i, 0, 1)[0] for i in range(nq)]
+    guard = 0xC0DE
+    buf = np.full(nq * (re - rb) * 31 + 62, guard, np.uint16)      # a guard row before and after the [nq][rows][31] block
+    view = buf[31:-31].reshape(nq, re - rb, 31)
+    iris.denominators_batch([iris.MasksEngine(q) for q in qms], db, rb, re, view)
+    assert np.array_equal(view, np.stack([O.masks_batch(q, masks[rb:re]) for q in qms]))
+    assert (buf[:31] == guard).all() and (buf[-31:] == guard).all()
+
+
+def test_four_query_kernel_unaligned_device_output(iris, shard):
+    import torch
+
+    db, masks = shard
+    nq, rb, re = 6, 129, 1400
+    qms = [O.gen_mask_rows(90 + i, 0, 1)[0] for i in range(nq)]
+    exp = np.stack([O.masks_batch(q, masks[rb:re]) for q in qms])
+    m = nq * (re - rb) * 31
+    for off in (1, 3, 5):
+        buf = torch.full((m + 64,), 0x7777, dtype=torch.int16, device="cuda")
+        iris.denominators_batch([iris.MasksEngine(q) for q in qms], db, rb, re, buf[off : off + m])
+        db.synchronize()
+        got = buf.cpu().numpy().view(np.uint16)
+        assert np.array_equal(got[off : off + m].reshape(nq, re - rb, 31), exp)
+        assert (got[:off] == 0x7777).all() and (got[off + m :] == 0x7777).all()
+
+
+def test_four_query_kernel_several_pairs_per_cta_every_row(iris):
+    import torch
+
+    n, nq = 150_000, 9                                          # two full groups of four + one left-over mask
+    with iris.Database(n, shares=False) as db:
+        db.generate(SEED, 0, n)
+        qms = [O.gen_mask_rows(100 + i, 1, 1)[0] for i in range(nq)]
+        out = torch.zeros((nq, n, 31), dtype=torch.int16, device="cuda")
+        for _ in range(2):
+            iris.denominators_batch([iris.MasksEngine(q) for q in qms], db, 0, n, out)
+        db.synchronize()
+        cn = torch.zeros((n, 31), dtype=torch.int16, device="cuda")
+        for k in range(nq):
+            db.check_denominators_simt(qms[k], 0, n, cn)
+            db.synchronize()
+            assert torch.equal(out[k], cn), k
+        host = out[5].cpu().numpy().view(np.uint16)
+        for i in (0, 255, 256, 75_775, 75_776, n - 1):
+            assert np.array_equal(host[i], O.masks_batch(qms[5], O.gen_mask_rows(SEED, int(i), 1))[0]), i
+
+
+_BATCH_VARIANT_SCRIPT = r"""
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, %r)
+import mpc_iris_code_b200 as iris
+n, nq = 20_000, 21
+with iris.Database(n, shares=False) as db:
+    db.generate(0x1715C0DE, 0, n)
+    qms = np.random.default_rng(77).integers(0, 2**64, size=(nq, 200), dtype=np.uint64)
+    out = np.zeros((nq, n - 77, 31), np.uint16)
+    iris.denominators_batch([iris.MasksEngine(q) for q in qms], db, 33, n - 44, out)
+    print(hashlib.sha256(out.tobytes()).hexdigest())
+"""
+
+
+def test_batched_kernel_variants_agree(iris):
+    """IRIS_BATCHDEN=i8 selects the int8 GEMM kernel for the batched denominators; identical bytes either way."""
+    digests = {}
+    for mode in ("", "i8"):
+        env = dict(os.environ)
+        env.pop("IRIS_BATCHDEN", None)
+        if mode:
+            env["IRIS_BATCHDEN"] = mode
+        res = subprocess.run([sys.executable, "-c", _BATCH_VARIANT_SCRIPT % ROOT], env=env, capture_output=True, text=True,
+                             timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        digests[mode] = res.stdout.strip().splitlines()[-1]
+    assert digests[""] == digests["i8"], digests
