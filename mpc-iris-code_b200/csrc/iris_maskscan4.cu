@@ -415,6 +415,8 @@ static_assert(kMqStages % 2 == 0 && kMqABars % 2 == 0, "each ring position alway
 
 enum MqWatchdog { kWqProducer = 521, kWqMmaFull = 522, kWqMmaA = 523, kWqMmaTmem = 524, kWqExpFull = 525, kWqExpA = 526, kWqEpilogue = 527 };
 
+// kFlags (diagnostics, wrong results): 2 = no expansion, 4 = no UMMAs, 8 = the epilogue frees the accumulator at once
+template <int kFlags>
 __global__ void __launch_bounds__(kMqThreads, 1) mask_scan_fp4_multi_kernel(const MultiMaskScanParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(kMqThreads, 1) mask_scan_fp4_multi_kernel(cons
             const uint32_t blo0 = ((qbase & 0x3FFFFu) >> 4) | (1u << 16);
             if (ptx::elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
+                for (int k = 0; k < ((kFlags & 4) ? 0 : 4); ++k)      // 64 nibbles = 32 bytes = 8 TMEM columns per step
                     umma_mxf4_ts(d, abase + k * 8, blo0 + ((32 * k) >> 4), kM4DescHiSw128, kMqIdesc, sf, (k | c) ? 1u : 0u);
                 ptx::umma_commit(aempty_bar(aj, t));
                 ptx::umma_commit(empty_bar(stage));
@@ -567,8 +569,10 @@ __global__ void __launch_bounds__(kMqThreads, 1) mask_scan_fp4_multi_kernel(cons
             if (lane == 0) ptx::mbar_arrive(empty_bar(stage));              // the packed bytes are in registers
             ptx::mbar_wait(aempty_bar(jw, t), wpar, p.error, kWqExpA);
             ptx::tc_fence_after();
-            tmem_st32_m4(tmem_base + lane_addr + kMqACol + ar * kM4ASlotCols + t * 32u, v);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (!(kFlags & 2)) {
+                tmem_st32_m4(tmem_base + lane_addr + kMqACol + ar * kM4ASlotCols + t * 32u, v);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(afull_bar(aj, t));
@@ -597,7 +601,7 @@ __global__ void __launch_bounds__(kMqThreads, 1) mask_scan_fp4_multi_kernel(cons
                     uint32_t a[32];
                     ptx::tmem_ld32(taddr + 32 * q, a);
                     ptx::tmem_wait_ld();
-                    if (q == kMaskMultiQueries - 1) {           // the accumulator is in registers: let the next tile start
+                    if (q == ((kFlags & 8) ? 0 : kMaskMultiQueries - 1)) {   // the accumulator is in registers: let the next tile start
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(tempty_bar(t));
@@ -623,22 +627,38 @@ __global__ void __launch_bounds__(kMqThreads, 1) mask_scan_fp4_multi_kernel(cons
     if (warp == kM4IssuerWarp0) ptx::tmem_dealloc(tmem_base, kM4TmemCols);
 }
 
-cudaError_t launch_mask_scan_fp4_multi(const MultiMaskScanParams& p, int num_sms, cudaStream_t stream) {
+template <int kFlags>
+static cudaError_t launch_mq_t(const MultiMaskScanParams& p, int num_sms, cudaStream_t stream) {
     static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(mask_scan_fp4_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMqSmemBytes);
+        e = cudaFuncSetAttribute(mask_scan_fp4_multi_kernel<kFlags>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMqSmemBytes);
         if (e != cudaSuccess) return e;
         if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     if (p.tile_end <= p.tile_begin) return cudaSuccess;
     const uint32_t pairs = (p.tile_end + kM4Tiles - 1) / kM4Tiles - p.tile_begin / kM4Tiles;
     const uint32_t grid = pairs < (uint32_t)num_sms ? pairs : (uint32_t)num_sms;
-    mask_scan_fp4_multi_kernel<<<grid, kMqThreads, kMqSmemBytes, stream>>>(p);
+    mask_scan_fp4_multi_kernel<kFlags><<<grid, kMqThreads, kMqSmemBytes, stream>>>(p);
     count_launch_external();
     return cudaGetLastError();
+}
+
+cudaError_t launch_mask_scan_fp4_multi(const MultiMaskScanParams& p, int num_sms, cudaStream_t stream) {
+    // IRIS_MQ_VARIANT selects a timing-only variant (flags above); unset = the product kernel.
+    static const int variant = [] {
+        const char* e = getenv("IRIS_MQ_VARIANT");
+        return e ? atoi(e) : 0;
+    }();
+    switch (variant) {
+        case 2: return launch_mq_t<2>(p, num_sms, stream);
+        case 4: return launch_mq_t<4>(p, num_sms, stream);
+        case 6: return launch_mq_t<6>(p, num_sms, stream);
+        case 8: return launch_mq_t<8>(p, num_sms, stream);
+        default: return launch_mq_t<0>(p, num_sms, stream);
+    }
 }
 
 // Query operand image for mask_scan_fp4_kernel: [stage s < 50][rotation slot r < 32][128 B, SWIZZLE_128B]; the 16-byte
