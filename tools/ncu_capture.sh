@@ -20,7 +20,7 @@ cap scan_distances 'scan_kernel' 4
 cap mask_scan_fp4 'mask_scan_fp4_kernel' 1
 cap batch_distances_s8 'batch_distances_kernel' 1
 cap batch_distances_u8 'batch_distances_kernel' 4
-cap batch_denominators 'batch_denominators_kernel' 1
+cap mask_scan_fp4_multi 'mask_scan_fp4_multi_kernel' 1
 cap combine_decode 'combine_decode_kernel' 0
 du -sh $OUT
 # launch list of the bench command itself (the timed region is the scan_kernel launches, one per step)

@@ -40,7 +40,7 @@ def main():
     for _ in range(3):
         iris.distances_batch(unif, db, 0, brows, big)      # batch_distances_kernel<0>
     for _ in range(3):
-        iris.denominators_batch(mes, db, 0, brows, big)    # batch_denominators_kernel
+        iris.denominators_batch(mes, db, 0, brows, big)    # mask_scan_fp4_multi_kernel x 16 (four masks per pass)
     db.synchronize()
     print("min/argmin:", iris.match_min(de, me, db, 0, rows))   # scan + combine_decode + final_min
     print("launches:", iris.launch_count())

@@ -11,10 +11,11 @@ C="python tools/profile_all.py 1000000 200000"
 timeout 300 $C > $OUT/plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches.csv $C > $OUT/launches.log 2>&1
 echo "launch list rc $?"
-ncu --set full --clock-control none --import-source on -k regex:mask_scan_fp4_kernel -s 1 -c 1 -o /tmp/m4 $C > $OUT/m4.log 2>&1
-echo "m4 rc $?"
-ncu -i /tmp/m4.ncu-rep --page raw --csv > $OUT/mask_scan_fp4_raw.csv 2>/dev/null
-ncu -i /tmp/m4.ncu-rep --page source --csv > $OUT/mask_scan_fp4_source.csv 2>/dev/null
+for K in mask_scan_fp4_kernel mask_scan_fp4_multi_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o /tmp/$K $C > $OUT/$K.log 2>&1
+  echo "$K rc $?"
+  ncu -i /tmp/$K.ncu-rep --page raw --csv > $OUT/${K}_raw.csv 2>/dev/null
+done
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras"
 timeout 300 $B > $OUT/bench_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bench.csv $B > $OUT/launches_bench.log 2>&1
 echo "bench launch list rc $?"
