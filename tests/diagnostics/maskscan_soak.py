@@ -55,6 +55,26 @@ def main():
             launches += reps
             checked += re - rb
         me.close()
+        # the batched path: groups of four masks on mask_scan_fp4_multi_kernel, left-overs on the single-query kernel
+        nq = int(rng.integers(2, 10))
+        qms = rng.integers(0, 2**64, size=(nq, 200), dtype=np.uint64)
+        mes = [iris.MasksEngine(q) for q in qms]
+        rb = int(rng.integers(0, rows - 1))
+        re = min(rows, rb + int(rng.integers(1, max(2, rows // nq))))
+        bout = got.reshape(-1)[: nq * (re - rb) * 31].view(nq, re - rb, 31)
+        bout.fill_(0x5A5A)
+        iris.denominators_batch(mes, db, rb, re, bout)
+        db.synchronize()
+        for k in range(nq):
+            db.check_denominators_simt(qms[k], rb, re, ref[: re - rb])
+            db.synchronize()
+            if not torch.equal(bout[k], ref[: re - rb]):
+                print(f"BATCH MISMATCH query {k} of {nq} rows [{rb},{re})", flush=True)
+                sys.exit(1)
+        for m in mes:
+            m.close()
+        launches += (nq + 3) // 4
+        checked += nq * (re - rb)
     print(f"soak ok: {launches} launches, {checked:,} rows compared in {time.time() - t0:.0f} s", flush=True)
 
 
