@@ -144,8 +144,9 @@ int iris_masks_engine_batch_process_resident(iris_masks_engine *e, uint16_t *out
 int iris_match_resident(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
                         uint64_t row_end, uint16_t *distances_out, uint16_t *denominators_out);
 
-/* ---- batched queries: num_queries DistanceEngines against the same rows as ONE dense int8 GEMM on
- * the tensor cores (BASELINE config 4).  Equivalent to calling batch_process_resident once per engine;
+/* ---- batched queries (BASELINE config 4): num_queries DistanceEngines against the same rows as ONE dense
+ * int8 GEMM on the tensor cores; num_queries MasksEngines four at a time over the 4-bit operand expanded into
+ * tensor memory.  Equivalent to calling batch_process_resident once per engine;
  * out = [num_queries][row_end-row_begin][31] u16, host or device memory. ---- */
 int iris_distances_batch_resident(iris_distance_engine *const *engines, uint32_t num_queries, iris_db *db,
                                   uint64_t row_begin, uint64_t row_end, uint16_t *out);

@@ -395,8 +395,8 @@ def distances_batch(engines, db: Database, row_begin: int, row_end: int, out) ->
 
 
 def denominators_batch(engines, db: Database, row_begin: int, row_end: int, out) -> None:
-    """All `engines` (MasksEngine list) against rows [row_begin,row_end) as one tensor-core GEMM;
-    out = [len(engines)][rows][31] u16."""
+    """All `engines` (MasksEngine list) against rows [row_begin,row_end), four query masks per pass of the 4-bit
+    tensor-core scan; out = [len(engines)][rows][31] u16."""
     n = len(engines) * (row_end - row_begin) * ROTATIONS
     arr = (ctypes.c_void_p * len(engines))(*[e._h.value for e in engines])
     _check(lib().iris_denominators_batch_resident(arr, len(engines), db._h, row_begin, row_end, _ptr(out, np.uint16, n, "out")))
