@@ -1,0 +1,66 @@
+"""Loose performance guards (1.5-2x the round-1 times on an idle B200: clocks ramp and boxes differ) so that a later change which silently
+falls off the fast path -- a kernel variant switch left on, a serialising sync, a lost overlap -- fails a test instead
+of only moving a bench number.  Times are CUDA-event means over back-to-back launches after a warm-up."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x1715C0DE
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+
+    import mpc_iris_code_b200 as iris
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("not enough free HBM for the 1 M-row shard")
+    rows = 1_000_000
+    stream = torch.cuda.Stream()
+    db = iris.Database(rows)
+    db.generate(SEED, 0, rows)
+    db.set_stream(stream.cuda_stream)
+    tmpl = np.random.default_rng(11).integers(0, 2**64, size=(16, 400), dtype=np.uint64)
+    yield iris, torch, stream, db, rows, tmpl
+    db.close()
+
+
+def _mean_ms(torch, stream, db, fn, warm, iters):
+    for _ in range(warm):
+        fn()
+    db.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
+    for _ in range(iters):
+        fn()
+    e.record(stream)
+    db.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def test_single_query_scans_stay_near_the_hbm_rate(ctx):
+    iris, torch, stream, db, rows, tmpl = ctx
+    de = iris.DistanceEngine.from_template(tmpl[0, :200].copy(), tmpl[0, 200:].copy())
+    me = iris.MasksEngine(tmpl[0, 200:].copy())
+    dist = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
+    den = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
+    fused = _mean_ms(torch, stream, db, lambda: iris.match(de, me, db, 0, rows, dist, den), 3, 10)
+    dists = _mean_ms(torch, stream, db, lambda: iris.match(de, None, db, 0, rows, dist, None), 3, 10)
+    masks = _mean_ms(torch, stream, db, lambda: iris.match(None, me, db, 0, rows, None, den), 50, 100)
+    assert fused < 6.0, f"fused scan {fused:.2f} ms per 1 M rows (round 1: 3.9)"
+    assert dists < 5.5, f"distances-only scan {dists:.2f} ms per 1 M rows (round 1: 3.6)"
+    assert masks < 0.6, f"denominators-only scan {masks:.3f} ms per 1 M rows (round 1: 0.28)"
+
+
+def test_batched_paths_stay_on_the_tensor_kernels(ctx):
+    iris, torch, stream, db, rows, tmpl = ctx
+    n = 200_000
+    des, mes = iris.engines_from_templates(tmpl)
+    out = torch.empty((16, n, 31), dtype=torch.int16, device="cuda")
+    dists = _mean_ms(torch, stream, db, lambda: iris.distances_batch(des, db, 0, n, out), 2, 5)
+    masks = _mean_ms(torch, stream, db, lambda: iris.denominators_batch(mes, db, 0, n, out), 2, 5)
+    assert dists < 4.0, f"16 queries x 200 k rows, distances: {dists:.2f} ms (round 1: 1.9)"
+    assert masks < 1.2, f"16 masks x 200 k rows, denominators: {masks:.2f} ms (round 1: 0.45)"
