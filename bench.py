@@ -293,6 +293,19 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     out["denominators_only_1q"] = dict(one_m, note="4-bit tcgen05 operands expanded into tensor memory (DESIGN.md 5.3); "
                                        "algorithmic bytes = 1 600 B read + 62 B written per row")
     out["denominators_sweep"] = sweep
+    # the reference's own calling pattern: batch_process on 20 000-row chunks (src/main.rs:427-430, 512-515), here as
+    # back-to-back asynchronous calls on the shard's stream with device outputs
+    chunk = 20_000
+
+    def chunked():
+        for c in range(0, rows, chunk):
+            e_ = min(rows, c + chunk)
+            iris.match(de, me, db, c, e_, d_dist[c:e_], d_den[c:e_])
+
+    ms = _time_ms(stream, chunked, db.synchronize, warmup=1, iters=5)
+    out["fused_in_20000_row_calls_1q"] = {"ms": ms, "calls": (rows + chunk - 1) // chunk, "comparisons_per_s": rows / (ms * 1e-3),
+                                          "note": "157 tiles of 128 rows on 148 SMs per call: one SM in sixteen scans two tiles; "
+                                                  "call with larger ranges when the caller allows it"}
     ms = _time_ms(stream, lambda: iris.match(de, None, db, 0, rows, d_dist, None), db.synchronize, warmup=3, iters=10)
     out["distances_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
                                 "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9, "sm_mhz": _NVML["last_mhz"]}
