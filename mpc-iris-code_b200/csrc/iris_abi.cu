@@ -98,6 +98,11 @@ struct iris_db {
     uint8_t* d_red = nullptr;        // match_min: results + reduction scratch
     uint64_t red_rows = 0;
     int* d_error = nullptr;
+    // device-output scans still possibly in flight on own_stream: [begin, end) byte ranges of their outputs.  A new scan
+    // whose outputs are disjoint from all of them may overlap their tails (programmatic dependent launch).
+    static constexpr int kChain = 6;
+    uintptr_t chain_lo[kChain][2] = {}, chain_hi[kChain][2] = {};
+    int chain_len = 0;
 };
 
 struct iris_distance_engine {
@@ -487,6 +492,25 @@ static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t
         p.row_end = row_end;
         p.tile_begin = (uint32_t)(row_begin / kTileRows);
         p.tile_end = (uint32_t)((row_end + kTileRows - 1) / kTileRows);
+        // The reference calls batch_process chunk after chunk (src/main.rs:427-430): consecutive scans on the library's
+        // own stream with disjoint outputs may overlap (the next one starts on the SMs the previous one's tail leaves
+        // idle).  After kChain chained launches one ordinary launch drains the chain, so the ranges below are all a
+        // running scan can belong to.  Never on a caller-supplied stream: its other work is unknown.
+        const size_t bytes = (size_t)(row_end - row_begin) * kOutRowBytes;
+        const uintptr_t lo[2] = {reinterpret_cast<uintptr_t>(dist_out), reinterpret_cast<uintptr_t>(den_out)};
+        const uintptr_t hi[2] = {dist_out ? lo[0] + bytes : 0, den_out ? lo[1] + bytes : 0};
+        bool chain = db->stream == db->own_stream && !raw_dev && db->chain_len < iris_db::kChain;
+        for (int i = 0; chain && i < db->chain_len; ++i)
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b)
+                    if (lo[a] < db->chain_hi[i][b] && db->chain_lo[i][b] < hi[a]) chain = false;
+        if (!chain) db->chain_len = 0;          // an ordinary launch waits for everything before it
+        p.pdl = chain && db->chain_len > 0;
+        for (int a = 0; a < 2; ++a) {
+            db->chain_lo[db->chain_len][a] = lo[a];
+            db->chain_hi[db->chain_len][a] = hi[a];
+        }
+        ++db->chain_len;
         CK(launch_scan(p, db->num_sms, db->stream));
         return IRIS_OK;
     }

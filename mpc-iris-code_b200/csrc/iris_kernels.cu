@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    ptx::pdl_launch_dependents();               // the next scan's CTAs may take the SMs this kernel leaves idle
 
     const uint32_t tile0 = p.tile_begin + blockIdx.x;
     const uint32_t tile_step = gridDim.x;
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::pdl_wait();                            // complete in stream order
 }
 
 template <bool S, bool M, bool SQ>
@@ -301,6 +303,20 @@ static cudaError_t launch_scan_t(const ScanParams& p, int num_sms, cudaStream_t 
     const uint32_t tiles = p.tile_end - p.tile_begin;
     if (tiles == 0) return cudaSuccess;
     const uint32_t grid = tiles < (uint32_t)num_sms ? tiles : (uint32_t)num_sms;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kScanThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        count_launch();
+        return cudaLaunchKernelEx(&cfg, scan_kernel<S, M, SQ>, p);
+    }
     scan_kernel<S, M, SQ><<<grid, kScanThreads, Cfg::kSmemBytes, stream>>>(p);
     count_launch();
     return cudaGetLastError();

@@ -22,6 +22,7 @@ struct ScanParams {
     uint32_t tile_end;       // = ceil(row_end / 128)
     int* error;              // device int, set by the watchdog
     bool signed_query;       // query elements are sign-extended bytes: two-product path (q_lo plane as s8)
+    bool pdl;                // launch with programmatic stream serialization (may overlap the previous scan's tail)
 };
 
 // Launches the persistent tcgen05 scan.  Mode is derived from which of shares/masks is non-null.

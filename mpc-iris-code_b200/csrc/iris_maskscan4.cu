@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     __syncthreads();
     ptx::tc_fence_after();
 
+    ptx::pdl_launch_dependents();               // the next scan's CTAs may take the SMs this kernel leaves idle
     constexpr bool kProf = (kFlags & 256) != 0;
     long long prof[3] = {0, 0, 0};
     const long long prof_t0 = kProf ? clock64() : 0;
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == kM4IssuerWarp0) ptx::tmem_dealloc(tmem_base, kM4TmemCols);
+    ptx::pdl_wait();                            // complete in stream order
 }
 
 template <int kFlags>
@@ -369,6 +371,20 @@ static cudaError_t launch_m4_t(const ScanParams& p, int num_sms, cudaStream_t st
     if (p.tile_end <= p.tile_begin) return cudaSuccess;
     const uint32_t pairs = (p.tile_end + kM4Tiles - 1) / kM4Tiles - p.tile_begin / kM4Tiles;
     const uint32_t grid = pairs < (uint32_t)num_sms ? pairs : (uint32_t)num_sms;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kP4Threads);
+        cfg.dynamicSmemBytes = kP4SmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        count_launch_external();
+        return cudaLaunchKernelEx(&cfg, mask_scan_fp4_kernel<kFlags>, p);
+    }
     mask_scan_fp4_kernel<kFlags><<<grid, kP4Threads, kP4SmemBytes, stream>>>(p);
     count_launch_external();
     return cudaGetLastError();

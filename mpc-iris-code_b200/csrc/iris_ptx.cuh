@@ -99,6 +99,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, i
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A scan launched with cudaLaunchAttributeProgrammaticStreamSerialization may start its CTAs as soon as every CTA of
+// the previous kernel in the stream has called pdl_launch_dependents() -- i.e. on the SMs that kernel's one-tile tail
+// leaves idle.  The scans are independent of each other (read-only database, disjoint outputs: the host checks), so
+// the dependency wait sits at the END of the kernel: it only keeps completion in stream order.  Both are no-ops in a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- bulk async copy (TMA engine, 1-D)
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
