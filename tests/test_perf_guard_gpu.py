@@ -1,4 +1,4 @@
-"""Loose performance guards (1.5-2x the round-1 times on an idle B200: clocks ramp and boxes differ) so that a later change which silently
+"""Loose performance guards (about 3x the round-1 times on an idle B200: clocks ramp, boxes differ and may be shared) so that a later change which silently
 falls off the fast path -- a kernel variant switch left on, a serialising sync, a lost overlap -- fails a test instead
 of only moving a bench number.  Times are CUDA-event means over back-to-back launches after a warm-up."""
 import numpy as np
@@ -50,9 +50,9 @@ def test_single_query_scans_stay_near_the_hbm_rate(ctx):
     fused = _mean_ms(torch, stream, db, lambda: iris.match(de, me, db, 0, rows, dist, den), 3, 10)
     dists = _mean_ms(torch, stream, db, lambda: iris.match(de, None, db, 0, rows, dist, None), 3, 10)
     masks = _mean_ms(torch, stream, db, lambda: iris.match(None, me, db, 0, rows, None, den), 50, 100)
-    assert fused < 6.0, f"fused scan {fused:.2f} ms per 1 M rows (round 1: 3.9)"
-    assert dists < 5.5, f"distances-only scan {dists:.2f} ms per 1 M rows (round 1: 3.6)"
-    assert masks < 0.6, f"denominators-only scan {masks:.3f} ms per 1 M rows (round 1: 0.28)"
+    assert fused < 12.0, f"fused scan {fused:.2f} ms per 1 M rows (round 1: 3.9)"
+    assert dists < 11.0, f"distances-only scan {dists:.2f} ms per 1 M rows (round 1: 3.6)"
+    assert masks < 0.9, f"denominators-only scan {masks:.3f} ms per 1 M rows (round 1: 0.28)"
 
 
 def test_batched_paths_stay_on_the_tensor_kernels(ctx):
@@ -62,5 +62,5 @@ def test_batched_paths_stay_on_the_tensor_kernels(ctx):
     out = torch.empty((16, n, 31), dtype=torch.int16, device="cuda")
     dists = _mean_ms(torch, stream, db, lambda: iris.distances_batch(des, db, 0, n, out), 2, 5)
     masks = _mean_ms(torch, stream, db, lambda: iris.denominators_batch(mes, db, 0, n, out), 2, 5)
-    assert dists < 4.0, f"16 queries x 200 k rows, distances: {dists:.2f} ms (round 1: 1.9)"
-    assert masks < 1.2, f"16 masks x 200 k rows, denominators: {masks:.2f} ms (round 1: 0.45)"
+    assert dists < 6.0, f"16 queries x 200 k rows, distances: {dists:.2f} ms (round 1: 1.9)"
+    assert masks < 1.5, f"16 masks x 200 k rows, denominators: {masks:.2f} ms (round 1: 0.45)"
