@@ -318,6 +318,25 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
                                           "note": "157 tiles of 128 rows on 148 SMs per call; on the library's own stream the "
                                                   "next call starts on the SMs the previous call's tail leaves idle, on a "
                                                   "caller-supplied stream the calls run strictly one after the other"}
+    # the coordinator's side of the same pattern: MasksEngine::batch_process on 20 000-row chunks (src/main.rs:512-515)
+    def chunked_masks():
+        for c in range(0, rows, chunk):
+            e_ = min(rows, c + chunk)
+            iris.match(None, me, db, c, e_, None, d_den[c:e_])
+
+    ms_serial = _steady_ms(stream, chunked_masks, db.synchronize, settle_s=0.2, iters=20)
+    db.set_stream(None)
+    for _ in range(20):
+        chunked_masks()
+    db.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        chunked_masks()
+    db.synchronize()
+    ms = (time.perf_counter() - t0) / 20 * 1e3
+    db.set_stream(stream.cuda_stream)
+    out["denominators_in_20000_row_calls_1q"] = {"ms": ms, "calls": (rows + chunk - 1) // chunk,
+                                                 "comparisons_per_s": rows / (ms * 1e-3), "ms_on_a_caller_stream": ms_serial}
     ms = _time_ms(stream, lambda: iris.match(de, None, db, 0, rows, d_dist, None), db.synchronize, warmup=3, iters=10)
     out["distances_only_1q"] = {"ms": ms, "comparisons_per_s": rows / (ms * 1e-3),
                                 "algorithmic_GBps": rows * 25662 / (ms * 1e-3) / 1e9, "sm_mhz": _NVML["last_mhz"]}
