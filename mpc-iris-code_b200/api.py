@@ -32,20 +32,24 @@ class IrisError(RuntimeError):
         self.code = code
 
 
+def _diagnostics_requested() -> bool:
+    return os.environ.get("IRIS_B200_DIAG_LIB", "") not in ("", "0")
+
+
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libiris_b200.so")
+    """The product library; IRIS_B200_DIAG_LIB=1 selects the diagnostics build (tests/diagnostics and the
+    kernel-variant tests only -- it carries A/B kernels and timing-only variants the product does not)."""
+    return os.path.join(_HERE, "lib", "libiris_b200_diag.so" if _diagnostics_requested() else "libiris_b200.so")
 
 
 def lib():
-    """Loads libiris_b200.so (building it with nvcc if it is absent).  No fallback."""
+    """Loads libiris_b200.so, (re)building it with nvcc when it is absent or older than its sources.  No fallback."""
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = library_path()
-    if not os.path.exists(path):
-        from . import build as _build
+    from . import build as _build
 
-        _build.build()
+    path = _build.build_diagnostics() if _diagnostics_requested() else _build.build()
     L = ctypes.CDLL(path)
     vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
     pp = ctypes.POINTER(ctypes.c_void_p)

@@ -1,11 +1,18 @@
 """Builds libiris_b200.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc.
 
-    python -m mpc_iris_code_b200.build        # or: python mpc-iris-code_b200/build.py
+    python -m mpc_iris_code_b200.build        # or: python mpc-iris-code_b200/build.py [--force] [-v] [--diag]
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the tree.
+
+Two libraries come out of the same sources:
+  lib/libiris_b200.so       the product.  No environment switches, no timing-only kernel variants.
+  lib/libiris_b200_diag.so  -DIRIS_DIAGNOSTICS: adds the superseded A/B kernels (iris_maskscan.cu, the int8 GEMM
+                            denominators) and the IRIS_* environment switches that tests/diagnostics and the
+                            "kernel variants agree" tests use.  Selected with IRIS_B200_DIAG_LIB=1, never by default.
 """
 from __future__ import annotations
 
+import fcntl
 import os
 import shutil
 import subprocess
@@ -15,8 +22,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libiris_b200.so")
-SOURCES = ["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan.cu", "iris_maskscan4.cu"]
-HEADERS = ["iris_layout.h", "iris_ptx.cuh", "iris_kernels.cuh", "iris_epilogue.cuh", "../../include/iris_b200.h"]
+DIAG_LIB_PATH = os.path.join(LIB_DIR, "libiris_b200_diag.so")
+SOURCES = ["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan4.cu", "iris_dotbatch.cu",
+           "iris_cluster.cu"]
+DIAG_SOURCES = SOURCES + ["iris_maskscan.cu"]
+HEADERS = ["iris_layout.h", "iris_ptx.cuh", "iris_kernels.cuh", "iris_epilogue.cuh", "iris_runtime.cuh",
+           "../../include/iris_b200.h"]
 
 NVCC_FLAGS = [
     "-O3",
@@ -27,8 +38,11 @@ NVCC_FLAGS = [
     "-Xcompiler",
     "-fPIC",
     "--expt-relaxed-constexpr",
+    "--threads",
+    "0",
     "-shared",
 ]
+LINK_FLAGS = ["-ldl", "-lpthread"]
 
 
 def find_nvcc() -> str:
@@ -38,31 +52,48 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _sources():
-    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+def _sources(names=SOURCES):
+    return [os.path.join(CSRC, s) for s in names if os.path.exists(os.path.join(CSRC, s))]
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def is_stale(lib_path: str = LIB_PATH, names=SOURCES) -> bool:
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + [os.path.join(CSRC, h) for h in HEADERS]
+    t = os.path.getmtime(lib_path)
+    deps = _sources(names) + [os.path.join(CSRC, h) for h in HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(lib_path: str, names, extra, verbose: bool) -> None:
+    os.makedirs(LIB_DIR, exist_ok=True)
+    # one builder at a time (torchrun ranks and pytest-xdist workers may all find a stale library)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not is_stale(lib_path, names) and not extra.get("force"):
+            return
+        tmp = lib_path + f".tmp{os.getpid()}"
+        cmd = [find_nvcc(), *NVCC_FLAGS, *extra.get("flags", []), "-o", tmp, *_sources(names), *LINK_FLAGS]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+        os.replace(tmp, lib_path)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB_PATH + f".tmp{os.getpid()}"
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", tmp, *_sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
-    os.replace(tmp, LIB_PATH)
+    _compile(LIB_PATH, SOURCES, {"force": force}, verbose)
     build_participant()
     return LIB_PATH
+
+
+def build_diagnostics(force: bool = False, verbose: bool = False) -> str:
+    """The diagnostics library (see the module docstring); not loaded unless IRIS_B200_DIAG_LIB=1."""
+    if not force and not is_stale(DIAG_LIB_PATH, DIAG_SOURCES):
+        return DIAG_LIB_PATH
+    _compile(DIAG_LIB_PATH, DIAG_SOURCES, {"force": force, "flags": ["-DIRIS_DIAGNOSTICS"]}, verbose)
+    return DIAG_LIB_PATH
 
 
 BIN_DIR = os.path.join(HERE, "bin")
@@ -89,4 +120,7 @@ def build_participant() -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--diag" in sys.argv:
+        print(build_diagnostics(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

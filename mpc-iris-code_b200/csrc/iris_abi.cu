@@ -85,7 +85,7 @@ static constexpr uint64_t kResultChunkTilesPerSm = 8;             // host-output
 struct iris_db {
     int device = 0;
     int num_sms = 148;
-    uint64_t capacity = 0;   // rows, multiple of 128
+    uint64_t capacity = 0;   // rows, multiple of 256
     uint32_t flags = 0;
     uint64_t n_shares = 0, n_masks = 0;
     uint8_t* d_shares = nullptr;
@@ -97,6 +97,9 @@ struct iris_db {
     uint64_t res_rows = 0;
     uint8_t* d_red = nullptr;        // match_min: results + reduction scratch
     uint64_t red_rows = 0;
+    // Watchdog flag: mapped page-locked HOST memory, so the code a trapping kernel leaves behind can still be read
+    // after the trap has poisoned the context.  h_error is the host view, d_error the device alias.
+    int* h_error = nullptr;
     int* d_error = nullptr;
     // device-output scans still possibly in flight on own_stream: [begin, end) byte ranges of their outputs.  A new scan
     // whose outputs are disjoint from all of them may overlap their tails (programmatic dependent launch).
@@ -105,58 +108,174 @@ struct iris_db {
     int chain_len = 0;
 };
 
+// Shards that are alive (engines remember the shard they last scanned so that their buffers are released in stream
+// order; a shard that has been destroyed was synchronised on the way out and needs no ordering any more).
+static std::mutex g_db_mu;
+static std::vector<iris_db*> g_live_dbs;
+static bool db_is_live(iris_db* db) {
+    std::lock_guard<std::mutex> g(g_db_mu);
+    return std::find(g_live_dbs.begin(), g_live_dbs.end(), db) != g_live_dbs.end();
+}
+
+// Everything one prepared query owns, pooled per (kind, device) so that engine construction per request performs no
+// cudaMalloc.  Release is STREAM-ORDERED: `used` is recorded behind the last scan that reads the operand images when
+// the engine is freed, and the next owner's preparation waits for it on the device -- iris_*_engine_free never
+// blocks and a scan that is still running keeps reading intact data.  `h` is page-locked staging owned by the slot:
+// the caller's query is copied into it before the call returns, so no caller pointer is retained.
+struct EngineSlot {
+    int device = -1;
+    uint8_t* d = nullptr;
+    uint8_t* h = nullptr;
+    cudaEvent_t ready = nullptr, used = nullptr;
+};
+enum SlotKind { kSlotDistance = 0, kSlotMasks = 1 };
+// distance slot, device: [qd 819 200][query 25 600][template 3 200]; host: [query 25 600][s8 flag]
+constexpr size_t kDSlotQuery = kQdBytes, kDSlotTemplate = kQdBytes + IRIS_BITS * 2;
+constexpr size_t kDSlotDevBytes = kDSlotTemplate + 2 * IRIS_MASK_BYTES, kDSlotHostBytes = IRIS_BITS * 2 + 64;
+// masks slot, device: [qm 409 600 | qm4 204 800][mask 1 600]; host: [mask 1 600]
+constexpr size_t kMSlotMask = kQmBytes + kQm4Bytes;
+constexpr size_t kMSlotDevBytes = kMSlotMask + 1664, kMSlotHostBytes = 1664;
+
+struct SlotPool {
+    std::mutex mu;
+    std::vector<EngineSlot> free_slots[2];
+    bool take(SlotKind kind, int dev, EngineSlot* out) {
+        std::lock_guard<std::mutex> g(mu);
+        auto& v = free_slots[kind];
+        for (size_t i = v.size(); i-- > 0;)
+            if (v[i].device == dev) {
+                *out = v[i];
+                v.erase(v.begin() + i);
+                return true;
+            }
+        return false;
+    }
+    bool give(SlotKind kind, const EngineSlot& s) {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_slots[kind].size() >= 512) return false;
+        free_slots[kind].push_back(s);
+        return true;
+    }
+};
+static SlotPool g_slots;
+
+static void slot_destroy(EngineSlot& s) {
+    if (s.used) cudaEventSynchronize(s.used);
+    if (s.ready) cudaEventSynchronize(s.ready);
+    if (s.d) cudaFree(s.d);
+    if (s.h) cudaFreeHost(s.h);
+    if (s.ready) cudaEventDestroy(s.ready);
+    if (s.used) cudaEventDestroy(s.used);
+    cudaGetLastError();
+    s = EngineSlot();
+}
+
+// A slot for a new engine; `stream` (the preparation stream) is made to wait for the previous owner's last scan.
+static int slot_acquire(SlotKind kind, int device, cudaStream_t stream, EngineSlot* out) {
+    if (g_slots.take(kind, device, out)) {
+        CK(cudaStreamWaitEvent(stream, out->used, 0));          // a never-recorded event is complete
+        return IRIS_OK;
+    }
+    EngineSlot s;
+    s.device = device;
+    auto body = [&]() -> int {
+        CK(cudaMalloc(&s.d, kind == kSlotDistance ? kDSlotDevBytes : kMSlotDevBytes));
+        CK(cudaHostAlloc(&s.h, kind == kSlotDistance ? kDSlotHostBytes : kMSlotHostBytes, cudaHostAllocPortable | cudaHostAllocMapped));
+        CK(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.used, cudaEventDisableTiming));
+        return IRIS_OK;
+    };
+    int rc = body();
+    if (rc) {
+        std::string keep = g_last_error;
+        slot_destroy(s);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = s;
+    return IRIS_OK;
+}
+
+struct EngineUse {                   // which shard's stream last read the operand images of an engine
+    iris_db* last_db = nullptr;
+    cudaStream_t ready_seen = nullptr;   // stream that already waits behind `ready`
+    bool ready_seen_valid = false;
+};
+
 struct iris_distance_engine {
     int device = 0;
+    EngineSlot slot;
     uint16_t* d_query = nullptr;
     uint8_t* d_qd = nullptr;
     bool fits_s8 = false;            // every element is a sign-extended byte (true for encode() output)
+    bool classified = true;          // false: the s8 flag is still being computed on the device (device-pointer query)
+    EngineUse use;
     iris_db* scratch = nullptr;      // for the host-slice batch_process
 };
 
 struct iris_masks_engine {
     int device = 0;
+    EngineSlot slot;
     uint8_t* d_qmask = nullptr;
     uint8_t* d_qm = nullptr;
+    EngineUse use;
     iris_db* scratch = nullptr;
 };
 
-// small free-list so that engine construction per query does not hit cudaMalloc every time
-struct BufPool {
-    std::mutex mu;
-    std::vector<std::pair<int, void*>> qd, qm, q16, q8;
-    void* take(std::vector<std::pair<int, void*>>& v, int dev) {
-        std::lock_guard<std::mutex> g(mu);
-        for (size_t i = 0; i < v.size(); ++i)
-            if (v[i].first == dev) {
-                void* p = v[i].second;
-                v.erase(v.begin() + i);
-                return p;
-            }
-        return nullptr;
+// Orders a scan on `db` behind the engine's preparation and remembers the shard for the stream-ordered release.
+static int engine_begin_use(EngineSlot& slot, EngineUse& use, iris_db* db) {
+    if (use.last_db && use.last_db != db && db_is_live(use.last_db)) {
+        // rare: one engine scanning several shards.  Make the new shard's stream follow the old one's, so that the
+        // single `used` record at release time covers both.
+        CK(cudaEventRecord(slot.used, use.last_db->stream));
+        CK(cudaStreamWaitEvent(db->stream, slot.used, 0));
     }
-    void give(std::vector<std::pair<int, void*>>& v, int dev, void* p) {
-        if (!p) return;
-        std::lock_guard<std::mutex> g(mu);
-        if (v.size() < 64) {
-            v.emplace_back(dev, p);
-            return;
-        }
-        cudaFree(p);
+    use.last_db = db;
+    if (!use.ready_seen_valid || use.ready_seen != db->stream) {
+        CK(cudaStreamWaitEvent(db->stream, slot.ready, 0));
+        use.ready_seen = db->stream;
+        use.ready_seen_valid = true;
     }
-};
-static BufPool g_pool;
+    return IRIS_OK;
+}
 
-static int pooled_alloc(std::vector<std::pair<int, void*>>& v, int dev, size_t bytes, void** out) {
-    void* p = g_pool.take(v, dev);
-    if (!p) CK(cudaMalloc(&p, bytes));
-    *out = p;
+static void engine_release(SlotKind kind, EngineSlot& slot, EngineUse& use) {
+    if (!slot.d) return;
+    if (use.last_db && db_is_live(use.last_db)) cudaEventRecord(slot.used, use.last_db->stream);
+    else cudaEventRecord(slot.used, cudaStreamPerThread);      // behind the preparation itself
+    cudaGetLastError();
+    if (!g_slots.give(kind, slot)) slot_destroy(slot);
+    slot = EngineSlot();
+}
+
+// Page-locked staging of the calling thread for multi-query uploads (per device; grown on demand, reused once the
+// previous upload from it has completed; lives as long as the thread -- never freed, it is one small buffer).
+struct ThreadStage {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+};
+static int thread_stage(int device, size_t bytes, ThreadStage** out) {
+    static thread_local ThreadStage stages[64];
+    if (device < 0 || device >= 64) return fail(IRIS_ERR_INVALID, "device %d out of range", device);
+    ThreadStage& st = stages[device];
+    if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(st.done));
+    if (st.cap < bytes) {
+        if (st.p) cudaFreeHost(st.p);
+        st.p = nullptr;
+        st.cap = 0;
+        CK(cudaHostAlloc(&st.p, bytes, cudaHostAllocPortable));
+        st.cap = bytes;
+    }
+    *out = &st;
     return IRIS_OK;
 }
 
 // Temporary device memory that lives for one ABI call: stream-ordered allocations (cudaStreamPerThread) from the
 // device's default pool, which is told to keep what it has been given.  After the first call of a kind no
 // cudaMalloc / cudaFree -- both of which synchronise the whole device -- is left on the per-query path.
-static int temp_alloc(int device, void** out, size_t bytes) {
+static int temp_alloc(int device, void** out, size_t bytes, cudaStream_t stream = cudaStreamPerThread) {
     static std::atomic<bool> tuned[64];
     if (device >= 0 && device < 64 && !tuned[device].load(std::memory_order_acquire)) {
         cudaMemPool_t pool;
@@ -165,11 +284,11 @@ static int temp_alloc(int device, void** out, size_t bytes) {
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         tuned[device].store(true, std::memory_order_release);
     }
-    CK(cudaMallocAsync(out, bytes ? bytes : 1, cudaStreamPerThread));
+    CK(cudaMallocAsync(out, bytes ? bytes : 1, stream));
     return IRIS_OK;
 }
-static void temp_free(void* p) {
-    if (p) cudaFreeAsync(p, cudaStreamPerThread);
+static void temp_free(void* p, cudaStream_t stream = cudaStreamPerThread) {
+    if (p) cudaFreeAsync(p, stream);
 }
 
 // ------------------------------------------------------------------------------------ database
@@ -207,8 +326,9 @@ extern "C" int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags
             CK(cudaEventCreateWithFlags(&db->ev_scan[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&db->ev_copy[i], cudaEventDisableTiming));
         }
-        CK(cudaMalloc(&db->d_error, sizeof(int)));
-        CK(cudaMemset(db->d_error, 0, sizeof(int)));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&db->h_error), 64, cudaHostAllocPortable | cudaHostAllocMapped));
+        *db->h_error = 0;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&db->d_error), db->h_error, 0));
         if (flags & IRIS_DB_SHARES) {
             CK(cudaMalloc(&db->d_shares, tiles * kShareTileBytes));
             CK(cudaMemsetAsync(db->d_shares, 0, tiles * kShareTileBytes, db->stream));
@@ -227,12 +347,20 @@ extern "C" int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags
         g_last_error = keep;
         return rc;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_db_mu);
+        g_live_dbs.push_back(db);
+    }
     *out = db;
     return IRIS_OK;
 }
 
 extern "C" int iris_db_destroy(iris_db* db) {
     if (!db) return IRIS_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_db_mu);
+        g_live_dbs.erase(std::remove(g_live_dbs.begin(), g_live_dbs.end(), db), g_live_dbs.end());
+    }
     DeviceGuard g(db->device);
     if (db->own_stream) cudaStreamSynchronize(db->own_stream);
     if (db->copy_stream) cudaStreamSynchronize(db->copy_stream);
@@ -240,7 +368,7 @@ extern "C" int iris_db_destroy(iris_db* db) {
     cudaFree(db->d_masks);
     cudaFree(db->d_stage);
     cudaFree(db->d_red);
-    cudaFree(db->d_error);
+    if (db->h_error) cudaFreeHost(db->h_error);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 2; ++k) cudaFree(db->d_res[b][k]);
     for (int i = 0; i < 2; ++i) {
@@ -275,18 +403,33 @@ extern "C" int iris_db_set_stream(iris_db* db, void* cuda_stream) {
     return IRIS_OK;
 }
 
+// The flag is host memory: reading it costs nothing and works after a trap has poisoned the context.
 static int check_error_flag(iris_db* db) {
-    int h = 0;
-    CK(cudaMemcpy(&h, db->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    const int h = *reinterpret_cast<volatile int*>(db->h_error);
     if (h != 0) return fail(IRIS_ERR_CUDA, "scan kernel watchdog fired (code %d)", h);
+    return IRIS_OK;
+}
+
+// synchronise a stream of this shard; a failure (e.g. the launch failure a watchdog trap leaves behind) reports the
+// watchdog code when there is one
+static int sync_checked(iris_db* db, cudaStream_t s) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        const int h = *reinterpret_cast<volatile int*>(db->h_error);
+        if (h != 0) return fail(IRIS_ERR_CUDA, "scan kernel watchdog fired (code %d): %s", h, cudaGetErrorString(e));
+        return fail(IRIS_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    }
     return IRIS_OK;
 }
 
 extern "C" int iris_db_synchronize(iris_db* db) {
     if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
     DeviceGuard g(db->device);
-    CK(cudaStreamSynchronize(db->stream));
-    CK(cudaStreamSynchronize(db->copy_stream));
+    int rc = sync_checked(db, db->stream);
+    if (rc) return rc;
+    rc = sync_checked(db, db->copy_stream);
+    if (rc) return rc;
     return check_error_flag(db);
 }
 
@@ -453,11 +596,22 @@ static int ensure_result_buffers(iris_db* db, uint64_t rows) {
     return IRIS_OK;
 }
 
-// qd / qm: prepared operand images (nullptr = that half is not computed).
-static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t row_begin, uint64_t row_end,
-                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev, bool signed_query = false) {
+// The s8 flag of an engine built from a DEVICE query is computed by a kernel; the first scan needs it on the host.
+static int engine_resolve(iris_distance_engine* e) {
+    if (e->classified) return IRIS_OK;
+    CK(cudaEventSynchronize(e->slot.ready));
+    e->fits_s8 = *reinterpret_cast<volatile int*>(e->slot.h + IRIS_BITS * 2) != 0;
+    e->classified = true;
+    return IRIS_OK;
+}
+
+// de / me: the engines whose operand images are scanned (nullptr = that half is not computed).
+static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* me, uint64_t row_begin, uint64_t row_end,
+                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev) {
     if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
-    if (!qd && !qm) return fail(IRIS_ERR_INVALID, "no engine given");
+    if (!de && !me) return fail(IRIS_ERR_INVALID, "no engine given");
+    const uint8_t* qd = de ? de->d_qd : nullptr;
+    const uint8_t* qm = me ? me->d_qm : nullptr;
     if (row_begin > row_end) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
     if (qd) {
         if (!db->d_shares) return fail(IRIS_ERR_STATE, "shard holds no shares");
@@ -471,6 +625,18 @@ static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t
     }
     if (row_begin == row_end) return IRIS_OK;
     DeviceGuard g(db->device);
+    bool signed_query = false;
+    if (de) {
+        int rc = engine_resolve(de);
+        if (rc) return rc;
+        signed_query = de->fits_s8;
+        rc = engine_begin_use(de->slot, de->use, db);
+        if (rc) return rc;
+    }
+    if (me) {
+        int rc = engine_begin_use(me->slot, me->use, db);
+        if (rc) return rc;
+    }
 
     ScanParams p{};
     p.shares = qd ? db->d_shares : nullptr;
@@ -551,8 +717,10 @@ static int scan_core(iris_db* db, const uint8_t* qd, const uint8_t* qm, uint64_t
         CK(cudaEventRecord(db->ev_copy[b], db->copy_stream));
         cb = ce;
     }
-    CK(cudaStreamSynchronize(db->copy_stream));
-    CK(cudaStreamSynchronize(db->stream));
+    int rc2 = sync_checked(db, db->copy_stream);
+    if (rc2) return rc2;
+    rc2 = sync_checked(db, db->stream);
+    if (rc2) return rc2;
     return check_error_flag(db);
 }
 
@@ -567,34 +735,69 @@ static int require_device(int device) {
     return IRIS_OK;
 }
 
+static int new_distance_engine(int device, cudaStream_t s, iris_distance_engine** out) {
+    iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
+    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    int rc = slot_acquire(kSlotDistance, device, s, &e->slot);
+    if (rc) {
+        delete e;
+        return rc;
+    }
+    e->d_qd = e->slot.d;
+    e->d_query = reinterpret_cast<uint16_t*>(e->slot.d + kDSlotQuery);
+    *out = e;
+    return IRIS_OK;
+}
+
+static int new_masks_engine(int device, cudaStream_t s, iris_masks_engine** out) {
+    iris_masks_engine* e = new (std::nothrow) iris_masks_engine();
+    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    int rc = slot_acquire(kSlotMasks, device, s, &e->slot);
+    if (rc) {
+        delete e;
+        return rc;
+    }
+    e->d_qm = e->slot.d;
+    e->d_qmask = e->slot.d + kMSlotMask;
+    *out = e;
+    return IRIS_OK;
+}
+
+// Engine construction is ASYNCHRONOUS: the query is copied into the slot's page-locked staging (so the caller's
+// buffer is free when the call returns), the upload and the preparation kernels are queued on the calling thread's
+// stream, and `ready` is recorded behind them; the first scan waits for it on the device.  No host synchronisation.
 extern "C" int iris_distance_engine_new(int device, const uint16_t* query, iris_distance_engine** out) {
     if (!query || !out) return fail(IRIS_ERR_INVALID, "NULL argument");
     *out = nullptr;
     int rc = require_device(device);
     if (rc) return rc;
     DeviceGuard g(device);
-    iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
-    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
-    e->device = device;
+    cudaStream_t s = cudaStreamPerThread;
+    iris_distance_engine* e = nullptr;
+    rc = new_distance_engine(device, s, &e);
+    if (rc) return rc;
     auto body = [&]() -> int {
-        int r = pooled_alloc(g_pool.q16, device, IRIS_BITS * sizeof(uint16_t), reinterpret_cast<void**>(&e->d_query));
-        if (r) return r;
-        r = pooled_alloc(g_pool.qd, device, kQdBytes, reinterpret_cast<void**>(&e->d_qd));
-        if (r) return r;
-        CK(cudaMemcpyAsync(e->d_query, query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDefault, cudaStreamPerThread));
-        CK(launch_prep_distance_query(e->d_query, e->d_qd, cudaStreamPerThread));
-        // classify the query for the batched path: sign-extended bytes need only two limb products
-        std::vector<uint16_t> host(IRIS_BITS);
-        const uint16_t* hq = query;
         if (is_device_pointer(query)) {
-            CK(cudaMemcpyAsync(host.data(), e->d_query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDeviceToHost, cudaStreamPerThread));
-            CK(cudaStreamSynchronize(cudaStreamPerThread));
-            hq = host.data();
+            // sign-extended bytes need only two limb products: classified on the device, read at the first scan
+            int* h_flag = reinterpret_cast<int*>(e->slot.h + IRIS_BITS * 2);
+            int* d_flag = nullptr;
+            *h_flag = 1;
+            CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_flag), h_flag, 0));
+            CK(cudaMemcpyAsync(e->d_query, query, IRIS_BITS * sizeof(uint16_t), cudaMemcpyDeviceToDevice, s));
+            CK(launch_classify_s8(e->d_query, d_flag, s));
+            e->classified = false;
+        } else {
+            uint16_t* st = reinterpret_cast<uint16_t*>(e->slot.h);
+            std::memcpy(st, query, IRIS_BITS * sizeof(uint16_t));
+            uint32_t bad = 0;
+            for (int k = 0; k < IRIS_BITS; ++k) bad |= (uint32_t)((uint16_t)(st[k] + 0x80u) > 0xFFu);
+            e->fits_s8 = bad == 0;
+            CK(cudaMemcpyAsync(e->d_query, st, IRIS_BITS * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
         }
-        bool s8 = true;
-        for (int k = 0; k < IRIS_BITS; ++k) s8 &= (hq[k] <= 0x7F) || (hq[k] >= 0xFF80);
-        e->fits_s8 = s8;
-        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        CK(launch_prep_distance_query(e->d_query, e->d_qd, s));
+        CK(cudaEventRecord(e->slot.ready, s));
         return IRIS_OK;
     };
     rc = body();
@@ -640,36 +843,27 @@ extern "C" int iris_distance_engine_new_from_template(int device, const uint64_t
     int rc = require_device(device);
     if (rc) return rc;
     DeviceGuard g(device);
-    iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
-    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
-    e->device = device;
-    uint8_t* d_t = nullptr;
+    cudaStream_t s = cudaStreamPerThread;
+    iris_distance_engine* e = nullptr;
+    rc = new_distance_engine(device, s, &e);
+    if (rc) return rc;
     auto body = [&]() -> int {
-        int r = pooled_alloc(g_pool.q16, device, IRIS_BITS * sizeof(uint16_t), reinterpret_cast<void**>(&e->d_query));
-        if (r) return r;
-        r = pooled_alloc(g_pool.qd, device, kQdBytes, reinterpret_cast<void**>(&e->d_qd));
-        if (r) return r;
-        r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&d_t));
-        if (r) return r;
-        uint8_t* d_m = nullptr;
-        r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&d_m));
-        if (r) return r;
-        int rr = IRIS_OK;
-        auto inner = [&]() -> int {
-            CK(cudaMemcpyAsync(d_t, pattern, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
-            CK(cudaMemcpyAsync(d_m, mask, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
-            CK(launch_encode(d_t, d_m, e->d_query, cudaStreamPerThread));
-            CK(launch_prep_distance_query(e->d_query, e->d_qd, cudaStreamPerThread));
-            CK(cudaStreamSynchronize(cudaStreamPerThread));
-            return IRIS_OK;
-        };
-        rr = inner();
-        g_pool.give(g_pool.q8, device, d_m);
+        uint8_t* d_t = e->slot.d + kDSlotTemplate;
+        if (is_device_pointer(pattern) || is_device_pointer(mask)) {
+            CK(cudaMemcpyAsync(d_t, pattern, IRIS_MASK_BYTES, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(d_t + IRIS_MASK_BYTES, mask, IRIS_MASK_BYTES, cudaMemcpyDefault, s));
+        } else {
+            std::memcpy(e->slot.h, pattern, IRIS_MASK_BYTES);
+            std::memcpy(e->slot.h + IRIS_MASK_BYTES, mask, IRIS_MASK_BYTES);
+            CK(cudaMemcpyAsync(d_t, e->slot.h, 2 * IRIS_MASK_BYTES, cudaMemcpyHostToDevice, s));
+        }
+        CK(launch_encode(d_t, d_t + IRIS_MASK_BYTES, e->d_query, s));
+        CK(launch_prep_distance_query(e->d_query, e->d_qd, s));
+        CK(cudaEventRecord(e->slot.ready, s));
         e->fits_s8 = true;                           // encode() only yields 0, 1, 0xFFFF
-        return rr;
+        return IRIS_OK;
     };
     rc = body();
-    g_pool.give(g_pool.q8, device, d_t);
     if (rc) {
         std::string keep = g_last_error;
         iris_distance_engine_free(e);
@@ -680,8 +874,8 @@ extern "C" int iris_distance_engine_new_from_template(int device, const uint64_t
     return IRIS_OK;
 }
 
-// Q engines of each kind from Q wire Templates in one go: one H2D copy (3 200 B per query), three launches, one
-// synchronisation -- instead of 2Q copies, 3Q launches and 3Q synchronisations.
+// Q engines of each kind from Q wire Templates in one go: one H2D copy (3 200 B per query) and three or four
+// launches per 64 queries, no synchronisation.
 extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templates, uint32_t num_queries,
                                                iris_distance_engine** distance_engines, iris_masks_engine** masks_engines) {
     if (!templates || !distance_engines) return fail(IRIS_ERR_INVALID, "NULL argument");
@@ -693,51 +887,53 @@ extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templ
     int rc = require_device(device);
     if (rc) return rc;
     DeviceGuard g(device);
+    cudaStream_t s = cudaStreamPerThread;
+    const size_t tbytes = (size_t)num_queries * 2 * IRIS_MASK_BYTES;
     uint8_t* d_t = nullptr;
-    rc = temp_alloc(device, reinterpret_cast<void**>(&d_t), (size_t)num_queries * 2 * IRIS_MASK_BYTES);
+    rc = temp_alloc(device, reinterpret_cast<void**>(&d_t), tbytes);
     if (rc) return rc;
     auto body = [&]() -> int {
-        CK(cudaMemcpyAsync(d_t, templates, (size_t)num_queries * 2 * IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
+        if (is_device_pointer(templates)) {
+            CK(cudaMemcpyAsync(d_t, templates, tbytes, cudaMemcpyDeviceToDevice, s));
+        } else {
+            ThreadStage* st = nullptr;
+            int r = thread_stage(device, tbytes, &st);
+            if (r) return r;
+            std::memcpy(st->p, templates, tbytes);
+            CK(cudaMemcpyAsync(d_t, st->p, tbytes, cudaMemcpyHostToDevice, s));
+            CK(cudaEventRecord(st->done, s));
+        }
         for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxPrepBatch) {
             const uint32_t nq = std::min<uint32_t>(kMaxPrepBatch, num_queries - q0);
             PrepBatchParams p{};
             p.templates = d_t + (size_t)q0 * 2 * IRIS_MASK_BYTES;
             p.n = nq;
             for (uint32_t i = 0; i < nq; ++i) {
-                iris_distance_engine* e = new (std::nothrow) iris_distance_engine();
-                if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+                iris_distance_engine* e = nullptr;
+                int r = new_distance_engine(device, s, &e);
+                if (r) return r;
                 distance_engines[q0 + i] = e;
-                e->device = device;
                 e->fits_s8 = true;                           // encode() only yields 0, 1, 0xFFFF
-                int r = pooled_alloc(g_pool.q16, device, IRIS_BITS * sizeof(uint16_t), reinterpret_cast<void**>(&e->d_query));
-                if (r) return r;
-                r = pooled_alloc(g_pool.qd, device, kQdBytes, reinterpret_cast<void**>(&e->d_qd));
-                if (r) return r;
                 p.query[i] = e->d_query;
                 p.qd[i] = e->d_qd;
                 if (masks_engines) {
-                    iris_masks_engine* m = new (std::nothrow) iris_masks_engine();
-                    if (!m) return fail(IRIS_ERR_NOMEM, "host allocation failed");
+                    iris_masks_engine* m = nullptr;
+                    r = new_masks_engine(device, s, &m);
+                    if (r) return r;
                     masks_engines[q0 + i] = m;
-                    m->device = device;
-                    r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&m->d_qmask));
-                    if (r) return r;
-                    r = pooled_alloc(g_pool.qm, device, kQmBytes + kQm4Bytes, reinterpret_cast<void**>(&m->d_qm));
-                    if (r) return r;
-                    CK(cudaMemcpyAsync(m->d_qmask, p.templates + (size_t)i * 2 * IRIS_MASK_BYTES + IRIS_MASK_BYTES, IRIS_MASK_BYTES,
-                                       cudaMemcpyDeviceToDevice, cudaStreamPerThread));
                     p.qm[i] = m->d_qm;
-                    CK(launch_prep_mask_query_fp4(m->d_qmask, m->d_qm + kQmBytes, cudaStreamPerThread));
                 }
             }
-            CK(launch_prep_batch(p, cudaStreamPerThread));
+            CK(launch_prep_batch(p, s));
+            for (uint32_t i = 0; i < nq; ++i) {
+                CK(cudaEventRecord(distance_engines[q0 + i]->slot.ready, s));
+                if (masks_engines) CK(cudaEventRecord(masks_engines[q0 + i]->slot.ready, s));
+            }
         }
-        CK(cudaStreamSynchronize(cudaStreamPerThread));
         return IRIS_OK;
     };
     rc = body();
     temp_free(d_t);
-    cudaStreamSynchronize(cudaStreamPerThread);
     if (rc) {
         std::string keep = g_last_error;
         for (uint32_t i = 0; i < num_queries; ++i) {
@@ -753,12 +949,13 @@ extern "C" int iris_engines_new_from_templates(int device, const uint64_t* templ
     return rc;
 }
 
+// Never blocks: the buffers go back to the pool with an event recorded behind the last scan that reads them, and
+// the next engine built from them waits for that event on the device.
 extern "C" int iris_distance_engine_free(iris_distance_engine* e) {
     if (!e) return IRIS_OK;
     DeviceGuard g(e->device);
     if (e->scratch) iris_db_destroy(e->scratch);
-    g_pool.give(g_pool.q16, e->device, e->d_query);
-    g_pool.give(g_pool.qd, e->device, e->d_qd);
+    engine_release(kSlotDistance, e->slot, e->use);
     delete e;
     return IRIS_OK;
 }
@@ -769,18 +966,19 @@ extern "C" int iris_masks_engine_new(int device, const uint64_t* query_mask, iri
     int rc = require_device(device);
     if (rc) return rc;
     DeviceGuard g(device);
-    iris_masks_engine* e = new (std::nothrow) iris_masks_engine();
-    if (!e) return fail(IRIS_ERR_NOMEM, "host allocation failed");
-    e->device = device;
+    cudaStream_t s = cudaStreamPerThread;
+    iris_masks_engine* e = nullptr;
+    rc = new_masks_engine(device, s, &e);
+    if (rc) return rc;
     auto body = [&]() -> int {
-        int r = pooled_alloc(g_pool.q8, device, IRIS_MASK_BYTES, reinterpret_cast<void**>(&e->d_qmask));
-        if (r) return r;
-        r = pooled_alloc(g_pool.qm, device, kQmBytes + kQm4Bytes, reinterpret_cast<void**>(&e->d_qm));
-        if (r) return r;
-        CK(cudaMemcpyAsync(e->d_qmask, query_mask, IRIS_MASK_BYTES, cudaMemcpyDefault, cudaStreamPerThread));
-        CK(launch_prep_mask_query(e->d_qmask, e->d_qm, cudaStreamPerThread));
-        CK(launch_prep_mask_query_fp4(e->d_qmask, e->d_qm + kQmBytes, cudaStreamPerThread));
-        CK(cudaStreamSynchronize(cudaStreamPerThread));
+        if (is_device_pointer(query_mask)) {
+            CK(cudaMemcpyAsync(e->d_qmask, query_mask, IRIS_MASK_BYTES, cudaMemcpyDeviceToDevice, s));
+        } else {
+            std::memcpy(e->slot.h, query_mask, IRIS_MASK_BYTES);
+            CK(cudaMemcpyAsync(e->d_qmask, e->slot.h, IRIS_MASK_BYTES, cudaMemcpyHostToDevice, s));
+        }
+        CK(launch_prep_mask_query(e->d_qmask, e->d_qm, e->d_qm + kQmBytes, s));
+        CK(cudaEventRecord(e->slot.ready, s));
         return IRIS_OK;
     };
     rc = body();
@@ -798,13 +996,83 @@ extern "C" int iris_masks_engine_free(iris_masks_engine* e) {
     if (!e) return IRIS_OK;
     DeviceGuard g(e->device);
     if (e->scratch) iris_db_destroy(e->scratch);
-    g_pool.give(g_pool.q8, e->device, e->d_qmask);
-    g_pool.give(g_pool.qm, e->device, e->d_qm);
+    engine_release(kSlotMasks, e->slot, e->use);
     delete e;
     return IRIS_OK;
 }
 
-static constexpr uint64_t kScratchRows = 4096;
+// ------------------------------------------------------------------------------------ literal host-slice batch_process
+// The reference's exact shape: `db` is a HOST slice.  Rows travel host -> staging -> re-tiled scratch shard -> scan ->
+// results -> host in chunks, double buffered: the upload and re-tiling of chunk i+1 (copy stream) overlap the scan and
+// the result download of chunk i (scan stream); one synchronisation at the end.  PCIe-bound by construction.
+static constexpr uint64_t kSliceChunkShares = 2048;        // 52 MB of EncodedBits per chunk
+static constexpr uint64_t kSliceChunkMasks = 32768;        // 52 MB of Bits per chunk
+
+struct SlicePipe {                                         // lives in the scratch shard of an engine
+    cudaEvent_t loaded[2] = {nullptr, nullptr}, scanned[2] = {nullptr, nullptr};
+};
+
+template <bool SHARES>
+static int slice_batch_process(iris_distance_engine* de, iris_masks_engine* me, iris_db*& scratch, int device,
+                               uint16_t* out, const void* rows, uint64_t n) {
+    const uint64_t chunk = SHARES ? kSliceChunkShares : kSliceChunkMasks;
+    const size_t row_bytes = SHARES ? IRIS_BITS * sizeof(uint16_t) : IRIS_MASK_BYTES;
+    // scratch shard: two halves of `cap` rows each, sized to the call (rounded to whole 256-row pair tiles)
+    const uint64_t cap = (std::min(n, chunk) + 255) / 256 * 256;
+    if (scratch && scratch->capacity < 2 * cap) {
+        iris_db_destroy(scratch);
+        scratch = nullptr;
+    }
+    if (!scratch) {
+        int rc = iris_db_create(device, 2 * cap, SHARES ? IRIS_DB_SHARES : IRIS_DB_MASKS, &scratch);
+        if (rc) return rc;
+    }
+    iris_db* db = scratch;
+    DeviceGuard g(device);
+    const uint64_t half = db->capacity / 2;
+    if (SHARES) db->n_shares = db->capacity; else db->n_masks = db->capacity;   // every row of the scratch is addressable
+    // device staging for two chunks of reference-layout rows, device results for two chunks
+    if (!db->d_stage) CK(cudaMalloc(&db->d_stage, 2 * half * row_bytes));
+    int rc = ensure_result_buffers(db, half);
+    if (rc) return rc;
+    SlicePipe pipe;
+    auto body = [&]() -> int {
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaEventCreateWithFlags(&pipe.loaded[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&pipe.scanned[b], cudaEventDisableTiming));
+        }
+        uint64_t i = 0;
+        for (uint64_t off = 0; off < n; off += half, ++i) {
+            const int b = (int)(i & 1);
+            const uint64_t m = std::min(half, n - off);
+            uint8_t* stage = static_cast<uint8_t*>(db->d_stage) + (size_t)b * half * row_bytes;
+            if (i >= 2) CK(cudaStreamWaitEvent(db->copy_stream, pipe.scanned[b], 0));    // half b free again
+            CK(cudaMemcpyAsync(stage, static_cast<const uint8_t*>(rows) + off * row_bytes, m * row_bytes, cudaMemcpyHostToDevice, db->copy_stream));
+            if (SHARES) CK(launch_retile_shares(reinterpret_cast<const uint16_t*>(stage), m, db->d_shares, (uint64_t)b * half, db->copy_stream));
+            else CK(launch_retile_masks(stage, m, db->d_masks, (uint64_t)b * half, db->copy_stream));
+            CK(cudaEventRecord(pipe.loaded[b], db->copy_stream));
+            CK(cudaStreamWaitEvent(db->stream, pipe.loaded[b], 0));
+            uint16_t* d_out = db->d_res[b][SHARES ? 0 : 1];
+            int r = scan_core(db, de, me, (uint64_t)b * half, (uint64_t)b * half + m, SHARES ? d_out : nullptr,
+                              SHARES ? nullptr : d_out, nullptr);
+            if (r) return r;
+            CK(cudaMemcpyAsync(out + off * IRIS_ROTATIONS, d_out, m * kOutRowBytes, cudaMemcpyDeviceToHost, db->stream));
+            CK(cudaEventRecord(pipe.scanned[b], db->stream));
+        }
+        return IRIS_OK;
+    };
+    rc = body();
+    int rc2 = sync_checked(db, db->copy_stream);
+    int rc3 = sync_checked(db, db->stream);
+    for (int b = 0; b < 2; ++b) {
+        if (pipe.loaded[b]) cudaEventDestroy(pipe.loaded[b]);
+        if (pipe.scanned[b]) cudaEventDestroy(pipe.scanned[b]);
+    }
+    if (rc) return rc;
+    if (rc2) return rc2;
+    if (rc3) return rc3;
+    return check_error_flag(db);
+}
 
 extern "C" int iris_distance_engine_batch_process(iris_distance_engine* e, uint16_t* out, uint64_t out_len,
                                                   const uint16_t* db, uint64_t db_len) {
@@ -813,21 +1081,8 @@ extern "C" int iris_distance_engine_batch_process(iris_distance_engine* e, uint1
     if (out_len != db_len) return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)db_len);
     if (db_len == 0) return IRIS_OK;
     if (!out || !db) return fail(IRIS_ERR_INVALID, "NULL slice");
-    if (!e->scratch) {
-        int rc = iris_db_create(e->device, kScratchRows, IRIS_DB_SHARES, &e->scratch);
-        if (rc) return rc;
-    }
-    for (uint64_t off = 0; off < db_len; off += kScratchRows) {
-        const uint64_t m = std::min(kScratchRows, db_len - off);
-        iris_db_clear(e->scratch);
-        int rc = iris_db_append_shares(e->scratch, db + off * IRIS_BITS, m);
-        if (rc) return rc;
-        rc = scan_core(e->scratch, e->d_qd, nullptr, 0, m, out + off * IRIS_ROTATIONS, nullptr, nullptr, e->fits_s8);
-        if (rc) return rc;
-        rc = iris_db_synchronize(e->scratch);
-        if (rc) return rc;
-    }
-    return IRIS_OK;
+    if (is_device_pointer(db) || is_device_pointer(out)) return fail(IRIS_ERR_INVALID, "batch_process takes HOST slices (use a resident shard for device data)");
+    return slice_batch_process<true>(e, nullptr, e->scratch, e->device, out, db, db_len);
 }
 
 extern "C" int iris_masks_engine_batch_process(iris_masks_engine* e, uint16_t* out, uint64_t out_len,
@@ -837,22 +1092,8 @@ extern "C" int iris_masks_engine_batch_process(iris_masks_engine* e, uint16_t* o
     if (out_len != db_len) return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)db_len);
     if (db_len == 0) return IRIS_OK;
     if (!out || !db) return fail(IRIS_ERR_INVALID, "NULL slice");
-    const uint64_t rows = kScratchRows * 16;
-    if (!e->scratch) {
-        int rc = iris_db_create(e->device, rows, IRIS_DB_MASKS, &e->scratch);
-        if (rc) return rc;
-    }
-    for (uint64_t off = 0; off < db_len; off += rows) {
-        const uint64_t m = std::min(rows, db_len - off);
-        iris_db_clear(e->scratch);
-        int rc = iris_db_append_masks(e->scratch, db + off * IRIS_LIMBS, m);
-        if (rc) return rc;
-        rc = scan_core(e->scratch, nullptr, e->d_qm, 0, m, nullptr, out + off * IRIS_ROTATIONS, nullptr);
-        if (rc) return rc;
-        rc = iris_db_synchronize(e->scratch);
-        if (rc) return rc;
-    }
-    return IRIS_OK;
+    if (is_device_pointer(db) || is_device_pointer(out)) return fail(IRIS_ERR_INVALID, "batch_process takes HOST slices (use a resident shard for device data)");
+    return slice_batch_process<false>(nullptr, e, e->scratch, e->device, out, db, db_len);
 }
 
 extern "C" int iris_distance_engine_batch_process_resident(iris_distance_engine* e, uint16_t* out, uint64_t out_len,
@@ -861,7 +1102,7 @@ extern "C" int iris_distance_engine_batch_process_resident(iris_distance_engine*
     if (e->device != db->device) return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
     if (row_end < row_begin || out_len != row_end - row_begin)
         return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)(row_end - row_begin));
-    return scan_core(db, e->d_qd, nullptr, row_begin, row_end, out, nullptr, nullptr, e->fits_s8);
+    return scan_core(db, e, nullptr, row_begin, row_end, out, nullptr, nullptr);
 }
 
 extern "C" int iris_masks_engine_batch_process_resident(iris_masks_engine* e, uint16_t* out, uint64_t out_len,
@@ -870,7 +1111,7 @@ extern "C" int iris_masks_engine_batch_process_resident(iris_masks_engine* e, ui
     if (e->device != db->device) return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
     if (row_end < row_begin || out_len != row_end - row_begin)
         return fail(IRIS_ERR_INVALID, "out.len() (%llu) != db.len() (%llu)", (unsigned long long)out_len, (unsigned long long)(row_end - row_begin));
-    return scan_core(db, nullptr, e->d_qm, row_begin, row_end, nullptr, out, nullptr);
+    return scan_core(db, nullptr, e, row_begin, row_end, nullptr, out, nullptr);
 }
 
 extern "C" int iris_match_resident(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
@@ -878,8 +1119,7 @@ extern "C" int iris_match_resident(iris_distance_engine* de, iris_masks_engine* 
     if (!db || (!de && !me)) return fail(IRIS_ERR_INVALID, "NULL handle");
     if ((de && de->device != db->device) || (me && me->device != db->device))
         return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
-    return scan_core(db, de ? de->d_qd : nullptr, me ? me->d_qm : nullptr, row_begin, row_end, distances_out,
-                     denominators_out, nullptr, de && de->fits_s8);
+    return scan_core(db, de, me, row_begin, row_end, distances_out, denominators_out, nullptr);
 }
 
 extern "C" int iris_distances(int device, const uint16_t* query, const uint16_t* entry, uint16_t* out) {
@@ -908,8 +1148,10 @@ extern "C" int iris_denominators(int device, const uint64_t* query, const uint64
 
 // ------------------------------------------------------------------------------------ batched queries (dense GEMM)
 constexpr uint32_t kBatchDistanceGroup = 8;     // queries per accumulator tile of batch_distances_kernel
+#ifdef IRIS_DIAGNOSTICS
 constexpr uint32_t kBatchMaskGroup = 16;        // query masks per accumulator tile of batch_denominators_kernel
 constexpr uint32_t kBatchMaskTailLoop = 10;     // left-over masks handled by the single-query scan instead
+#endif
 extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engines, uint32_t num_queries, iris_db* db,
                                              uint64_t row_begin, uint64_t row_end, uint16_t* out) {
     if (!engines || !db) return fail(IRIS_ERR_INVALID, "NULL argument");
@@ -928,7 +1170,15 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
     const bool out_dev = is_device_pointer(out);
     uint16_t* d_out = out;
     const size_t out_bytes = (size_t)num_queries * rows * kOutRowBytes;
-    if (!out_dev) CK(cudaMalloc(&d_out, out_bytes + 64));
+    for (uint32_t i = 0; i < num_queries; ++i) {
+        int rc0 = engine_resolve(engines[i]);
+        if (!rc0) rc0 = engine_begin_use(engines[i]->slot, engines[i]->use, db);
+        if (rc0) return rc0;
+    }
+    if (!out_dev) {                      // host result: device staging from the stream-ordered pool (no cudaMalloc per call)
+        int rc0 = temp_alloc(db->device, reinterpret_cast<void**>(&d_out), out_bytes + 64, db->stream);
+        if (rc0) return rc0;
+    }
     auto body = [&]() -> int {
         for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxBatchQueries) {
             const uint32_t nq = std::min<uint32_t>(kMaxBatchQueries, num_queries - q0);
@@ -936,8 +1186,8 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
             // are used; a single left-over query is cheaper on the HBM-bound single-query scan (~3.6 ms).
             if (nq % kBatchDistanceGroup == 1) {
                 iris_distance_engine* e = engines[q0 + nq - 1];
-                int rc1 = scan_core(db, e->d_qd, nullptr, row_begin, row_end,
-                                    d_out + (size_t)(q0 + nq - 1) * rows * IRIS_ROTATIONS, nullptr, nullptr, e->fits_s8);
+                int rc1 = scan_core(db, e, nullptr, row_begin, row_end,
+                                    d_out + (size_t)(q0 + nq - 1) * rows * IRIS_ROTATIONS, nullptr, nullptr);
                 if (rc1) return rc1;
                 if (nq == 1) continue;
             }
@@ -960,16 +1210,16 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
         }
         if (!out_dev) {
             CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, db->stream));
-            CK(cudaStreamSynchronize(db->stream));
+            temp_free(d_out, db->stream);
+            d_out = nullptr;
+            int rc1 = sync_checked(db, db->stream);
+            if (rc1) return rc1;
             return check_error_flag(db);
         }
         return IRIS_OK;
     };
     int rc = body();
-    if (!out_dev) {
-        cudaStreamSynchronize(db->stream);
-        cudaFree(d_out);
-    }
+    if (!out_dev && d_out) temp_free(d_out, db->stream);
     return rc;
 }
 
@@ -991,13 +1241,24 @@ extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engine
     const bool out_dev = is_device_pointer(out);
     uint16_t* d_out = out;
     const size_t out_bytes = (size_t)num_queries * rows * kOutRowBytes;
-    if (!out_dev) CK(cudaMalloc(&d_out, out_bytes + 64));
-    // Default: four query masks per pass of the 4-bit TMEM-operand scan (mask_scan_fp4_multi_kernel); a single left-over
-    // mask goes to the single-query scan.  IRIS_BATCHDEN=i8 selects the int8 GEMM kernel (A/B measurements).
+    for (uint32_t i = 0; i < num_queries; ++i) {
+        int rc0 = engine_begin_use(engines[i]->slot, engines[i]->use, db);
+        if (rc0) return rc0;
+    }
+    if (!out_dev) {
+        int rc0 = temp_alloc(db->device, reinterpret_cast<void**>(&d_out), out_bytes + 64, db->stream);
+        if (rc0) return rc0;
+    }
+    // Four query masks per pass of the 4-bit TMEM-operand scan (mask_scan_fp4_multi_kernel); a single left-over mask
+    // goes to the single-query scan.  (Diagnostics build only: IRIS_BATCHDEN=i8 selects the int8 GEMM kernel.)
+#ifdef IRIS_DIAGNOSTICS
     static const bool use_i8_gemm = [] {
         const char* e = getenv("IRIS_BATCHDEN");
         return e && e[0] == 'i';
     }();
+#else
+    constexpr bool use_i8_gemm = false;
+#endif
     auto body = [&]() -> int {
         if (!use_i8_gemm) {
             uint32_t q = 0;
@@ -1020,11 +1281,13 @@ extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engine
                 CK(launch_mask_scan_fp4_multi(p, db->num_sms, db->stream));
             }
             for (; q < num_queries; ++q) {      // at most one mask is left
-                int rc1 = scan_core(db, nullptr, engines[q]->d_qm, row_begin, row_end, nullptr,
+                int rc1 = scan_core(db, nullptr, engines[q], row_begin, row_end, nullptr,
                                     d_out + (size_t)q * rows * IRIS_ROTATIONS, nullptr);
                 if (rc1) return rc1;
             }
-        } else
+        }
+#ifdef IRIS_DIAGNOSTICS
+        else
         for (uint32_t q0 = 0; q0 < num_queries; q0 += kMaxBatchQueries) {
             const uint32_t nq = std::min<uint32_t>(kMaxBatchQueries, num_queries - q0);
             // A group of 16 query masks costs one pass of the int8 GEMM (~3.2 ms per 1 M rows) however few of its
@@ -1033,7 +1296,7 @@ extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engine
             const uint32_t tail = nq % kBatchMaskGroup;
             const uint32_t nb = tail <= kBatchMaskTailLoop ? nq - tail : nq;
             for (uint32_t i = nb; i < nq; ++i) {
-                int rc1 = scan_core(db, nullptr, engines[q0 + i]->d_qm, row_begin, row_end, nullptr,
+                int rc1 = scan_core(db, nullptr, engines[q0 + i], row_begin, row_end, nullptr,
                                     d_out + (size_t)(q0 + i) * rows * IRIS_ROTATIONS, nullptr);
                 if (rc1) return rc1;
             }
@@ -1050,18 +1313,19 @@ extern "C" int iris_denominators_batch_resident(iris_masks_engine* const* engine
             p.error = db->d_error;
             CK(launch_batch_denominators(p, db->num_sms, db->stream));
         }
+#endif
         if (!out_dev) {
             CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, db->stream));
-            CK(cudaStreamSynchronize(db->stream));
+            temp_free(d_out, db->stream);
+            d_out = nullptr;
+            int rc1 = sync_checked(db, db->stream);
+            if (rc1) return rc1;
             return check_error_flag(db);
         }
         return IRIS_OK;
     };
     int rc = body();
-    if (!out_dev) {
-        cudaStreamSynchronize(db->stream);
-        cudaFree(d_out);
-    }
+    if (!out_dev && d_out) temp_free(d_out, db->stream);
     return rc;
 }
 
@@ -1268,7 +1532,7 @@ extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engi
     uint8_t* scratch = db->d_red + 2 * row_bytes;
     void* result = scratch + (combine_scratch_bytes(n) / 16) * 16 + 16;
     if (n) {
-        int rc = scan_core(db, de->d_qd, me->d_qm, row_begin, row_end, d_dist, d_den, nullptr, de->fits_s8);
+        int rc = scan_core(db, de, me, row_begin, row_end, d_dist, d_den, nullptr);
         if (rc) return rc;
     }
     CombineParams p{};
@@ -1383,7 +1647,7 @@ extern "C" int iris_debug_raw_accumulators(iris_distance_engine* de, iris_masks_
     auto body = [&]() -> int {
         CK(cudaMemsetAsync(d_raw, 0xEE, tiles * kTileRows * 128 * sizeof(int32_t), db->stream));
         uint16_t* d_den = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(d_o) + (n * kOutRowBytes + 63) / 64 * 64);
-        int rc = scan_core(db, de ? de->d_qd : nullptr, me ? me->d_qm : nullptr, row_begin, row_end, d_o, d_den, d_raw);
+        int rc = scan_core(db, de, me, row_begin, row_end, d_o, d_den, d_raw);
         if (rc) return rc;
         CK(cudaMemcpyAsync(raw_out, d_raw, tiles * kTileRows * 128 * sizeof(int32_t), cudaMemcpyDeviceToHost, db->stream));
         CK(cudaStreamSynchronize(db->stream));

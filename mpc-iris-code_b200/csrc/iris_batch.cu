@@ -261,6 +261,7 @@ cudaError_t launch_batch_distances(const BatchParams& p, bool signed_queries, in
     return signed_queries ? launch_batch_t<true>(p, num_sms, stream) : launch_batch_t<false>(p, num_sms, stream);
 }
 
+#ifdef IRIS_DIAGNOSTICS   // superseded by mask_scan_fp4_multi_kernel; kept in the diagnostics build for A/B runs
 // =====================================================================================
 // batched denominators: popcount(rot(qmask_g, j-15) & dbmask_i) for 16 query masks per cluster tile.
 // A = database mask bits expanded to bytes inside the SM (one LOP per 4 bytes, value 2^t, see
@@ -491,5 +492,7 @@ cudaError_t launch_batch_denominators(const BatchMaskParams& p, int num_sms, cud
     count_launch_external();
     return cudaGetLastError();
 }
+
+#endif  // IRIS_DIAGNOSTICS
 
 }  // namespace iris

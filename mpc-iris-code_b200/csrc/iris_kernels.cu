@@ -329,20 +329,22 @@ cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
     if (s) return p.signed_query ? launch_scan_t<true, false, true>(p, num_sms, stream)
                                  : launch_scan_t<true, false, false>(p, num_sms, stream);
     if (m) {
-        // denominators only: the TMEM-operand kernels -- 4-bit operands (iris_maskscan4.cu) when the engine carries
-        // that image, else int8 (iris_maskscan.cu).  IRIS_MASKSCAN=i8 / smem select the int8 TMEM kernel / the
-        // shared-memory-operand variant of this file (kept for A/B measurements and the raw debug dump).
+        // denominators only: the 4-bit TMEM-operand kernel (iris_maskscan4.cu).  The shared-memory-operand variant of
+        // this file serves the raw debug dump (and engines without the 4-bit image).
+        if (p.raw_out || !p.qm4) return launch_scan_t<false, true, false>(p, num_sms, stream);
+#ifdef IRIS_DIAGNOSTICS
+        // Diagnostics build only: IRIS_MASKSCAN=i8 / smem select the int8 TMEM kernel (iris_maskscan.cu) / the
+        // shared-memory-operand kernel for A/B measurements.
         static const char mode = [] {
             const char* e = getenv("IRIS_MASKSCAN");
             return e ? e[0] : 'f';
         }();
-        if (mode == 's' || p.raw_out) return launch_scan_t<false, true, false>(p, num_sms, stream);
-        if (mode != 'i' && p.qm4) {
-            ScanParams p4 = p;
-            p4.qm = p.qm4;
-            return launch_mask_scan_fp4(p4, num_sms, stream);
-        }
-        return launch_mask_scan(p, num_sms, stream);
+        if (mode == 's') return launch_scan_t<false, true, false>(p, num_sms, stream);
+        if (mode == 'i') return launch_mask_scan(p, num_sms, stream);
+#endif
+        ScanParams p4 = p;
+        p4.qm = p.qm4;
+        return launch_mask_scan_fp4(p4, num_sms, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -472,7 +474,19 @@ cudaError_t launch_prep_batch(const PrepBatchParams& p, cudaStream_t stream) {
     if (p.qm[0]) {
         prep_mask_batch_kernel<<<dim3((kChunks * 32 * 8 + 255) / 256, p.n), 256, 0, stream>>>(p);
         count_launch();
+        cudaError_t e = launch_prep_mask_fp4_batch(p, stream);
+        if (e != cudaSuccess) return e;
     }
+    return cudaGetLastError();
+}
+
+__global__ void classify_s8_kernel(const uint16_t* __restrict__ q, int* __restrict__ flag) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < IRIS_BITS && (uint16_t)(q[k] + 0x80u) > 0xFFu) *flag = 0;
+}
+cudaError_t launch_classify_s8(const uint16_t* d_query, int* d_flag, cudaStream_t stream) {
+    classify_s8_kernel<<<(IRIS_BITS + 255) / 256, 256, 0, stream>>>(d_query, d_flag);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -481,10 +495,10 @@ cudaError_t launch_prep_distance_query(const uint16_t* d_query, uint8_t* d_qd, c
     count_launch();
     return cudaGetLastError();
 }
-cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, cudaStream_t stream) {
+cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, uint8_t* d_qm4, cudaStream_t stream) {
     prep_mask_query_kernel<<<(kChunks * 32 * 8 + 255) / 256, 256, 0, stream>>>(d_qmask, d_qm);
     count_launch();
-    return cudaGetLastError();
+    return launch_prep_mask_query_fp4(d_qmask, d_qm4, stream);
 }
 
 // =====================================================================================

@@ -58,7 +58,12 @@ struct PrepBatchParams {
     uint32_t n;
 };
 cudaError_t launch_prep_batch(const PrepBatchParams& p, cudaStream_t stream);
-cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, cudaStream_t stream);
+// 4-bit images of the same batch (iris_maskscan4.cu): p.qm[i] + kQmBytes receives the image of query i.
+cudaError_t launch_prep_mask_fp4_batch(const PrepBatchParams& p, cudaStream_t stream);
+// Both mask operand images of one query: the int8 image (fused scan) and the 4-bit image (denominators-only scan).
+cudaError_t launch_prep_mask_query(const uint8_t* d_qmask, uint8_t* d_qm, uint8_t* d_qm4, cudaStream_t stream);
+// *d_flag (preset to 1) is cleared unless every element of the query is a sign-extended byte.
+cudaError_t launch_classify_s8(const uint16_t* d_query, int* d_flag, cudaStream_t stream);
 
 // Loader: reference-layout rows (device staging) -> tiled HBM image, starting at global row row0.
 cudaError_t launch_retile_shares(const uint16_t* d_rows, uint64_t n, uint8_t* d_shares, uint64_t row0,

@@ -391,7 +391,9 @@ static cudaError_t launch_m4_t(const ScanParams& p, int num_sms, cudaStream_t st
 }
 
 cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t stream) {
-    // IRIS_M4_VARIANT selects a diagnostic variant (flags above); unset = the product kernel.
+#ifdef IRIS_DIAGNOSTICS
+    // Diagnostics build only (libiris_b200_diag.so, -DIRIS_DIAGNOSTICS): IRIS_M4_VARIANT selects a timing-only or
+    // profiling variant (flags above; 2 / 4 / 6 return WRONG results).  The product library has no such switch.
     static const int variant = [] {
         const char* e = getenv("IRIS_M4_VARIANT");
         return e ? atoi(e) : 0;
@@ -401,8 +403,10 @@ cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t 
         case 4: return launch_m4_t<4>(p, num_sms, stream);
         case 6: return launch_m4_t<6>(p, num_sms, stream);
         case 256: return launch_m4_t<256>(p, num_sms, stream);
-        default: return launch_m4_t<0>(p, num_sms, stream);
+        default: break;
     }
+#endif
+    return launch_m4_t<0>(p, num_sms, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -663,7 +667,8 @@ static cudaError_t launch_mq_t(const MultiMaskScanParams& p, int num_sms, cudaSt
 }
 
 cudaError_t launch_mask_scan_fp4_multi(const MultiMaskScanParams& p, int num_sms, cudaStream_t stream) {
-    // IRIS_MQ_VARIANT selects a timing-only variant (flags above); unset = the product kernel.
+#ifdef IRIS_DIAGNOSTICS
+    // Diagnostics build only: IRIS_MQ_VARIANT selects a timing-only variant (flags above, WRONG results).
     static const int variant = [] {
         const char* e = getenv("IRIS_MQ_VARIANT");
         return e ? atoi(e) : 0;
@@ -673,16 +678,16 @@ cudaError_t launch_mask_scan_fp4_multi(const MultiMaskScanParams& p, int num_sms
         case 4: return launch_mq_t<4>(p, num_sms, stream);
         case 6: return launch_mq_t<6>(p, num_sms, stream);
         case 8: return launch_mq_t<8>(p, num_sms, stream);
-        default: return launch_mq_t<0>(p, num_sms, stream);
+        default: break;
     }
+#endif
+    return launch_mq_t<0>(p, num_sms, stream);
 }
 
 // Query operand image for mask_scan_fp4_kernel: [stage s < 50][rotation slot r < 32][128 B, SWIZZLE_128B]; the 16-byte
 // chunk `ch` of a row holds the output words 4 * ch + t (t = 0..3) of input word ch; nibble j of word t stands for
 // the bit 256 * s + 32 * ch + 4 * j + t of rot(qmask, r - 15) and holds 2.0, 1.0, 0.5, 0.5 (e2m1) for t = 0..3.
-__global__ void prep_mask_query_fp4_kernel(const uint8_t* __restrict__ qmask, uint8_t* __restrict__ qm4) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (s, r, ch)
-    if (idx >= kM4StagesPerTile * 32 * 8) return;
+__device__ __forceinline__ void prep_mask_fp4_body(const uint8_t* __restrict__ qmask, uint8_t* __restrict__ qm4, int idx) {
     const int ch = idx & 7, r = (idx >> 3) & 31, s = idx >> 8;
     uint32_t out[4] = {0, 0, 0, 0};
     if (r < IRIS_ROTATIONS) {
@@ -701,8 +706,26 @@ __global__ void prep_mask_query_fp4_kernel(const uint8_t* __restrict__ qmask, ui
     const size_t off = (size_t)s * kQm4StageBytes + r * 128 + ((ch ^ (r & 7)) << 4);
     *reinterpret_cast<uint4*>(qm4 + off) = make_uint4(out[0], out[1], out[2], out[3]);
 }
+__global__ void prep_mask_query_fp4_kernel(const uint8_t* __restrict__ qmask, uint8_t* __restrict__ qm4) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (s, r, ch)
+    if (idx >= kM4StagesPerTile * 32 * 8) return;
+    prep_mask_fp4_body(qmask, qm4, idx);
+}
 cudaError_t launch_prep_mask_query_fp4(const uint8_t* d_qmask, uint8_t* d_qm4, cudaStream_t stream) {
     prep_mask_query_fp4_kernel<<<(kM4StagesPerTile * 32 * 8 + 255) / 256, 256, 0, stream>>>(d_qmask, d_qm4);
+    count_launch_external();
+    return cudaGetLastError();
+}
+// The same for a batch of wire Templates (mask = second half of each 3 200-byte Template).
+__global__ void prep_mask_fp4_batch_kernel(const PrepBatchParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (s, r, ch)
+    if (idx >= kM4StagesPerTile * 32 * 8) return;
+    const uint32_t qi = blockIdx.y;
+    prep_mask_fp4_body(p.templates + (size_t)qi * 2 * IRIS_MASK_BYTES + IRIS_MASK_BYTES, p.qm[qi] + kQmBytes, idx);
+}
+cudaError_t launch_prep_mask_fp4_batch(const PrepBatchParams& p, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    prep_mask_fp4_batch_kernel<<<dim3((kM4StagesPerTile * 32 * 8 + 255) / 256, p.n), 256, 0, stream>>>(p);
     count_launch_external();
     return cudaGetLastError();
 }

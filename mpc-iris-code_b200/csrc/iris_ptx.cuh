@@ -61,7 +61,18 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 // Wait with a watchdog: a protocol bug must surface as a trapped launch with an error code,
-// never as a hung GPU.  `code` identifies the waiting role.
+// never as a hung GPU.  `code` identifies the waiting role.  The flag lives in MAPPED PINNED HOST memory
+// (iris_db::h_error), so the code is still readable after the trap has poisoned the context.  The limit is
+// wall-clock (globaltimer) and generous: a healthy wait is microseconds, but a time-sliced or replayed (ncu)
+// kernel can be descheduled for long stretches.
+constexpr unsigned long long kWatchdogNs = 20000000000ull;
+__device__ __forceinline__ void watchdog_fire(int* err, int code) {
+    if (err) {
+        *reinterpret_cast<volatile int*>(err) = code;
+        __threadfence_system();
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
     if (mbar_try_wait(bar, parity)) return;
     uint64_t t0 = 0;
@@ -71,11 +82,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
             if (mbar_try_wait(bar, parity)) return;
         const uint64_t now = globaltimer_ns();
         if (t0 == 0) t0 = now;
-        if (now - t0 > 4000000000ull) {
-            if (err) atomicExch(err, code);
-            __threadfence_system();
-            __trap();
-        }
+        if (now - t0 > kWatchdogNs) watchdog_fire(err, code);
     }
 }
 
@@ -90,11 +97,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, i
         if ((++spins & 0x3FF) == 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            if (now - t0 > 4000000000ull) {
-                if (err) atomicExch(err, code);
-                __threadfence_system();
-                __trap();
-            }
+            if (now - t0 > kWatchdogNs) watchdog_fire(err, code);
         }
     }
 }
@@ -242,11 +245,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
     uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if ((++spins & 0x3FF) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-            if (err) atomicExch(err, code);
-            __threadfence_system();
-            __trap();
-        }
+        if ((++spins & 0x3FF) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_fire(err, code);
     }
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {

@@ -46,7 +46,7 @@ uint16_t oracle_dot_bool(const uint64_t *a, const uint64_t *b) {
 uint16_t oracle_dot_u16(const uint16_t *a, const uint16_t *b) {
     uint16_t acc = 0;
     for (int i = 0; i < IRIS_BITS; ++i)
-        acc = (uint16_t)(acc + (uint16_t)(a[i] * b[i]));
+        acc = (uint16_t)(acc + (uint16_t)((uint32_t)a[i] * (uint32_t)b[i])); /* u32: u16*u16 promoted to int would overflow */
     return acc;
 }
 

@@ -134,17 +134,38 @@ with iris.Database(n, shares=False) as db:
 
 
 def test_kernel_variants_agree(iris):
-    """IRIS_MASKSCAN selects the int8 TMEM-operand kernel ('i8') or the shared-memory-operand kernel ('smem'); the
-    library reads it once, so each variant runs in its own process.  All three must produce identical bytes."""
+    """The diagnostics build (libiris_b200_diag.so, IRIS_B200_DIAG_LIB=1) keeps the superseded kernels behind
+    IRIS_MASKSCAN: the int8 TMEM-operand kernel ('i8') and the shared-memory-operand kernel ('smem').  The library
+    reads the switch once, so each variant runs in its own process.  All of them, and the product library (which has
+    no switch at all), must produce identical bytes."""
     digests = {}
-    for mode in ("f", "i8", "smem"):
-        env = dict(os.environ, IRIS_MASKSCAN=mode)
-        env.pop("IRIS_M4_VARIANT", None)
+    for mode in ("product", "f", "i8", "smem"):
+        env = dict(os.environ)
+        for k in ("IRIS_MASKSCAN", "IRIS_M4_VARIANT", "IRIS_B200_DIAG_LIB"):
+            env.pop(k, None)
+        if mode != "product":
+            env.update(IRIS_MASKSCAN=mode, IRIS_B200_DIAG_LIB="1")
         res = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % ROOT], env=env, capture_output=True, text=True,
-                             timeout=300)
+                             timeout=600)
         assert res.returncode == 0, res.stderr[-2000:]
         digests[mode] = res.stdout.strip().splitlines()[-1]
-    assert digests["f"] == digests["i8"] == digests["smem"], digests
+    assert len(set(digests.values())) == 1, digests
+
+
+def test_product_library_ignores_diagnostic_switches(iris):
+    """A stray IRIS_M4_VARIANT / IRIS_MQ_VARIANT (timing-only kernels with WRONG results in the diagnostics build)
+    must not change what the product library computes."""
+    digests = []
+    for extra in ({}, {"IRIS_M4_VARIANT": "6", "IRIS_MQ_VARIANT": "6", "IRIS_MASKSCAN": "i8", "IRIS_BATCHDEN": "i8"}):
+        env = dict(os.environ)
+        for k in ("IRIS_MASKSCAN", "IRIS_M4_VARIANT", "IRIS_MQ_VARIANT", "IRIS_BATCHDEN", "IRIS_B200_DIAG_LIB"):
+            env.pop(k, None)
+        env.update(extra)
+        res = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % ROOT], env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        digests.append(res.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -218,15 +239,19 @@ with iris.Database(n, shares=False) as db:
 
 
 def test_batched_kernel_variants_agree(iris):
-    """IRIS_BATCHDEN=i8 selects the int8 GEMM kernel for the batched denominators; identical bytes either way."""
+    """Diagnostics build: IRIS_BATCHDEN=i8 selects the int8 GEMM kernel for the batched denominators; identical bytes
+    either way, and identical to the product library."""
     digests = {}
-    for mode in ("", "i8"):
+    for mode in ("product", "", "i8"):
         env = dict(os.environ)
-        env.pop("IRIS_BATCHDEN", None)
-        if mode:
+        for k in ("IRIS_BATCHDEN", "IRIS_MQ_VARIANT", "IRIS_B200_DIAG_LIB"):
+            env.pop(k, None)
+        if mode != "product":
+            env["IRIS_B200_DIAG_LIB"] = "1"
+        if mode == "i8":
             env["IRIS_BATCHDEN"] = mode
         res = subprocess.run([sys.executable, "-c", _BATCH_VARIANT_SCRIPT % ROOT], env=env, capture_output=True, text=True,
-                             timeout=300)
+                             timeout=600)
         assert res.returncode == 0, res.stderr[-2000:]
         digests[mode] = res.stdout.strip().splitlines()[-1]
-    assert digests[""] == digests["i8"], digests
+    assert len(set(digests.values())) == 1, digests
