@@ -65,6 +65,14 @@ uint64_t iris_launch_count(void);
  * parity only -- one launch per pair cannot amortise; use the engines for throughput. ---- */
 int iris_dot_u16(int device, const uint16_t a[IRIS_BITS], const uint16_t b[IRIS_BITS], uint16_t *out);
 int iris_dot_bool(int device, const uint64_t a[IRIS_LIMBS], const uint64_t b[IRIS_LIMBS], uint16_t *out);
+/* ---- arch-level grids: the reference's criterion benchmark (src/arch/mod.rs:22-72) calls dot_u16 / dot_bool on
+ * every pair of n_a INDEPENDENT vectors `a` and n_b vectors `b` (31 x 100 000 for dot_u16).  Here the whole grid is
+ * one call: out[i][j] = dot(a[j], b[i]), out = [n_b][n_a] u16.  Groups of 31 vectors of `a` take the place of the 31
+ * rotations of a query in the same tensor-core kernels the engines use.  a, b, out: host or device memory. ---- */
+int iris_dot_u16_batch(int device, const uint16_t *a /* [n_a][12800] */, uint32_t n_a, const uint16_t *b /* [n_b][12800] */,
+                       uint64_t n_b, uint16_t *out);
+int iris_dot_bool_batch(int device, const uint64_t *a /* [n_a][200] */, uint32_t n_a, const uint64_t *b /* [n_b][200] */,
+                        uint64_t n_b, uint16_t *out);
 
 /* ---- database shard: what the reference mmaps as &[EncodedBits] (src/main.rs:389-391) and
  * &[Bits] (src/main.rs:458-461), loaded ONCE into HBM and re-tiled for the tensor pipeline. ---- */
@@ -87,12 +95,26 @@ int iris_db_load_masks_file(iris_db *db, const char *path, uint64_t first_row, u
  * shard) produced on the device by a counter-based generator keyed by (seed, row id);
  * row ids are first_row_id, first_row_id+1, ...  (oracle/iris_oracle.c restates the generator). */
 int iris_db_generate(iris_db *db, uint64_t seed, uint64_t first_row_id, uint64_t n);
+/* The same synthetic database, but with shares that MEAN something: row id R is the synthetic Template
+ * (pattern_R, mask_R), mask_R being the mask row iris_db_generate produces; its encoding (src/lib.rs:16-26) is split into
+ * n_parties additive shares as EncodedBits::share does (src/encoded_bits.rs:23-38: n-1 uniform vectors, the last one
+ * the encoding minus their sum), and this shard receives party `party`'s rows.  n_parties = 1 stores the plaintext
+ * encodings (the n = 1 sharing).  Masks are generated too when the shard holds masks. */
+int iris_db_generate_shares(iris_db *db, uint64_t seed, uint32_t party, uint32_t n_parties, uint64_t first_row_id,
+                            uint64_t n);
+/* Overwrite rows [row, row+n) that are already loaded (an enrolment update; reference layouts, host pointers). */
+int iris_db_write_shares(iris_db *db, uint64_t row, const uint16_t *rows /* [n][12800] */, uint64_t n);
+int iris_db_write_masks(iris_db *db, uint64_t row, const uint64_t *rows /* [n][200] */, uint64_t n);
 /* Read rows back in the reference layouts (inverse of the loader; tests and debugging). */
 int iris_db_read_shares(iris_db *db, uint64_t row_begin, uint64_t n, uint16_t *out /* [n][12800] */);
 int iris_db_read_masks(iris_db *db, uint64_t row_begin, uint64_t n, uint64_t *out /* [n][200] */);
 /* Run all work of this shard on the given cudaStream_t (NULL = the library's own stream). */
 int iris_db_set_stream(iris_db *db, void *cuda_stream);
+int iris_db_get_stream(iris_db *db, void **cuda_stream);
+int iris_db_device(const iris_db *db, int *device);
 int iris_db_synchronize(iris_db *db);
+/* Watchdog state of a shard whose stream the caller has synchronised itself. */
+int iris_db_check(iris_db *db);
 
 /* ---- page-locked host buffers for result slices.  The reference allocates a fresh Vec per chunk
  * (src/main.rs:429, 514); any host memory works here too, but device->host copies into page-locked
@@ -153,6 +175,13 @@ int iris_distances_batch_resident(iris_distance_engine *const *engines, uint32_t
 int iris_denominators_batch_resident(iris_masks_engine *const *engines, uint32_t num_queries, iris_db *db,
                                      uint64_t row_begin, uint64_t row_end, uint16_t *out);
 
+/* The arch-level grids (see iris_dot_u16_batch) against rows [row_begin,row_end) of a resident shard taking the place of
+ * `b`: out = [row_end-row_begin][n_a] u16, host or device; asynchronous on the shard's stream for a device `out`. */
+int iris_dot_u16_batch_resident(const uint16_t *a, uint32_t n_a, iris_db *db, uint64_t row_begin, uint64_t row_end,
+                                uint16_t *out);
+int iris_dot_bool_batch_resident(const uint64_t *a, uint32_t n_a, iris_db *db, uint64_t row_begin, uint64_t row_end,
+                                 uint16_t *out);
+
 /* ---- coordinator reduction on the device (src/main.rs:597-621 with decode_distance, src/lib.rs:97-107):
  * numerator = wrapping sum of the parties' distance shares; distance = min over rotations of
  * ((den - num) as u16 / 2) / den in f64 (NaN ignored); running min with `<` (first minimum wins;
@@ -170,6 +199,70 @@ int iris_combine_min_batch(int device, const uint16_t *distances, const uint16_t
  * the per-shard step of the multi-GPU path (each rank reduces its rows, the pairs are all-gathered). */
 int iris_match_min_resident(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
                             uint64_t row_end, uint64_t index_base, double *min_distance, uint64_t *min_index);
+
+/* Asynchronous form: the {f64 min_distance, u64 min_index} pair (16 bytes) is written to `result` -- device memory of
+ * this GPU, of a peer GPU (NVLink store), or mapped host memory -- in stream order on the shard's stream. */
+int iris_match_min_resident_async(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
+                                  uint64_t row_end, uint64_t index_base, void *result);
+/* Batched search on one shard (BASELINE configs[3]/[4] per GPU): num_queries (<= 64) engine pairs against rows
+ * [row_begin,row_end): batched tensor-core distances + denominators slice by slice into scratch owned by the shard,
+ * decode + min/argmin on the device, running min over the slices; results = [num_queries] x {f64, u64} written in
+ * stream order like above. */
+int iris_search_batch_resident_async(iris_distance_engine *const *des, iris_masks_engine *const *mes,
+                                     uint32_t num_queries, iris_db *db, uint64_t row_begin, uint64_t row_end,
+                                     uint64_t index_base, void *results);
+
+/* ---- cluster: ONE database row-sharded over several GPUs of the box (BASELINE configs[4]; the reference's mmap of
+ * the whole share file, src/main.rs:386-400, becomes contiguous row blocks in the HBM of each GPU).  The library runs
+ * one host thread and one stream per GPU.  Rows are independent, so the scan needs no collective; what is exchanged
+ * are the small per-query vectors:
+ *   - search: each shard's (min, argmin) pairs are stored by its reduction kernel straight into the root GPU's memory
+ *     over NVLink (peer stores; mapped host memory when the GPUs cannot reach each other) and merged there;
+ *   - match: every shard's scan kernel stores its [rows][31] result block at its row offset of ONE caller array, which
+ *     may live on any GPU of the cluster (peer stores) or in (pinned) host memory (one PCIe link per GPU in parallel);
+ *   - several processes (one per GPU, e.g. under torchrun) join one cluster with iris_cluster_join: the merged pairs
+ *     of each process are all-gathered over NCCL (libnccl.so.2, loaded at run time) and merged again.
+ * `devices` may name a GPU more than once (several shards on one GPU; used by the tests on one-GPU boxes). ---- */
+typedef struct iris_cluster iris_cluster;
+int iris_cluster_create(const int *devices, uint32_t n_devices, uint64_t capacity_rows, uint32_t flags,
+                        iris_cluster **out);
+int iris_cluster_destroy(iris_cluster *c);
+/* Contiguous block of shard `shard` when n_total rows are spread over n_shards (sizes differ by at most one row). */
+int iris_cluster_partition(uint64_t n_total, uint32_t n_shards, uint32_t shard, uint64_t *row_begin, uint64_t *row_end);
+/* Shard i of the cluster: its handle (usable with every iris_db_* / engine call), device and block of cluster rows. */
+int iris_cluster_shard(iris_cluster *c, uint32_t shard, iris_db **db, int *device, uint64_t *row_begin, uint64_t *row_end);
+int iris_cluster_len(const iris_cluster *c, uint32_t *n_shards, uint64_t *n_shares, uint64_t *n_masks);
+/* Populate (each replaces what the cluster held): n rows spread evenly, every GPU loading its block in parallel.
+ * n_parties = 0: uniform shares (iris_db_generate); otherwise iris_db_generate_shares.  Files are the reference's
+ * formats (see iris_db_load_*_file); either path may be NULL. */
+int iris_cluster_generate(iris_cluster *c, uint64_t seed, uint32_t party, uint32_t n_parties, uint64_t first_row_id,
+                          uint64_t n);
+int iris_cluster_load_files(iris_cluster *c, const char *shares_path, const char *masks_path);
+int iris_cluster_load_rows(iris_cluster *c, const uint16_t *shares /* [n][12800] or NULL */,
+                           const uint64_t *masks /* [n][200] or NULL */, uint64_t n);
+/* Row ids reported by searches are index_base + cluster row (a process of a multi-process cluster sets its offset). */
+int iris_cluster_set_index_base(iris_cluster *c, uint64_t index_base);
+/* One query against every row: DistanceEngine::new(query).batch_process and/or MasksEngine::new(mask).batch_process
+ * over the whole cluster (src/main.rs:425-431, 510-516).  query / query_mask: host memory (either may be NULL with its
+ * output); outputs = [n][31] u16 in host memory or on any GPU of the cluster.  Returns when the outputs are complete. */
+int iris_cluster_match(iris_cluster *c, const uint16_t *query, const uint64_t *query_mask, uint16_t *distances_out,
+                       uint16_t *denominators_out);
+/* The participant's request (src/main.rs:419-431): encode(&template) on each GPU, distances of the whole cluster. */
+int iris_cluster_match_template(iris_cluster *c, const uint64_t *pattern, const uint64_t *mask, uint16_t *distances_out,
+                                uint16_t *denominators_out);
+/* Search: num_queries wire Templates ([num_queries][400] u64 = {pattern[200], mask[200]}) against a cluster that
+ * holds whole encodings (n_parties = 1): per query the minimum decoded distance over all rows and rotations and the
+ * row attaining it (lowest row on ties; UINT64_MAX when nothing is below +inf) -- the coordinator's loop
+ * (src/main.rs:597-621) over every shard.  One query takes the fused HBM-bound scan, several the batched tensor-core
+ * path.  Only num_queries x 16 bytes leave the GPUs. */
+int iris_cluster_search(iris_cluster *c, const uint64_t *templates, uint32_t num_queries, double *min_distance,
+                        uint64_t *min_index);
+/* Multi-process clusters: rank 0 draws an id (128 bytes), every process receives it by any channel and joins.
+ * Afterwards iris_cluster_search is a collective call (same num_queries everywhere) and returns the global result in
+ * every process. */
+#define IRIS_UNIQUE_ID_BYTES 128
+int iris_comm_unique_id(void *id_out /* [128] */);
+int iris_cluster_join(iris_cluster *c, const void *unique_id, int rank, int world_size);
 
 /* ---- single-pair wrappers: src/lib.rs:82-87 and :89-94 ---- */
 int iris_distances(int device, const uint16_t query[IRIS_BITS], const uint16_t entry[IRIS_BITS],

@@ -10,6 +10,11 @@ There is no CPU fallback: every compute call goes through libiris_b200.so and fa
 from .api import (  # noqa: F401
     BITS,
     COLS,
+    Cluster,
+    cluster_partition,
+    comm_unique_id,
+    dot_bool_batch,
+    dot_u16_batch,
     LIMBS,
     ROTATIONS,
     ROWS,

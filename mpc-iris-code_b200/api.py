@@ -64,6 +64,32 @@ def lib():
         "iris_db_append_shares": [vp, vp, u64],
         "iris_db_append_masks": [vp, vp, u64],
         "iris_db_generate": [vp, u64, u64, u64],
+        "iris_db_generate_shares": [vp, u64, u32, u32, u64, u64],
+        "iris_db_write_shares": [vp, u64, vp, u64],
+        "iris_db_write_masks": [vp, u64, vp, u64],
+        "iris_db_get_stream": [vp, pp],
+        "iris_db_device": [vp, ctypes.POINTER(i32)],
+        "iris_db_check": [vp],
+        "iris_dot_u16_batch": [i32, vp, u32, vp, u64, vp],
+        "iris_dot_bool_batch": [i32, vp, u32, vp, u64, vp],
+        "iris_dot_u16_batch_resident": [vp, u32, vp, u64, u64, vp],
+        "iris_dot_bool_batch_resident": [vp, u32, vp, u64, u64, vp],
+        "iris_match_min_resident_async": [vp, vp, vp, u64, u64, u64, vp],
+        "iris_search_batch_resident_async": [vp, vp, u32, vp, u64, u64, u64, vp],
+        "iris_cluster_create": [ctypes.POINTER(i32), u32, u64, u32, pp],
+        "iris_cluster_destroy": [vp],
+        "iris_cluster_partition": [u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)],
+        "iris_cluster_shard": [vp, u32, pp, ctypes.POINTER(i32), ctypes.POINTER(u64), ctypes.POINTER(u64)],
+        "iris_cluster_len": [vp, ctypes.POINTER(u32), ctypes.POINTER(u64), ctypes.POINTER(u64)],
+        "iris_cluster_generate": [vp, u64, u32, u32, u64, u64],
+        "iris_cluster_load_files": [vp, ctypes.c_char_p, ctypes.c_char_p],
+        "iris_cluster_load_rows": [vp, vp, vp, u64],
+        "iris_cluster_set_index_base": [vp, u64],
+        "iris_cluster_match": [vp, vp, vp, vp, vp],
+        "iris_cluster_match_template": [vp, vp, vp, vp, vp],
+        "iris_cluster_search": [vp, vp, u32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
+        "iris_comm_unique_id": [vp],
+        "iris_cluster_join": [vp, vp, i32, i32],
         "iris_db_load_shares_file": [vp, ctypes.c_char_p, u64, u64],
         "iris_db_load_masks_file": [vp, ctypes.c_char_p, u64, u64],
         "iris_db_read_shares": [vp, u64, u64, vp],
@@ -169,19 +195,55 @@ def dot_bool(a, b, device: int = 0) -> int:
     return int(out[0])
 
 
+def dot_u16_batch(a, b, out=None, device: int = 0):
+    """The reference's criterion grid for dot_u16 (src/arch/mod.rs:46-72) in one call: a = [n_a][12800] u16 independent
+    vectors, b = [n_b][12800] u16 (or a resident Database); returns out[i][j] = dot_u16(a[j], b[i]), [n_b][n_a] u16."""
+    n_a = _numel(a) // BITS
+    if isinstance(b, Database):
+        n_b = b.len_shares
+        out = np.empty((n_b, n_a), np.uint16) if out is None else out
+        _check(lib().iris_dot_u16_batch_resident(_ptr(a, np.uint16, n_a * BITS, "a"), n_a, b._h, 0, n_b, _ptr(out, np.uint16, n_a * n_b, "out")))
+        return out
+    n_b = _numel(b) // BITS
+    out = np.empty((n_b, n_a), np.uint16) if out is None else out
+    _check(lib().iris_dot_u16_batch(device, _ptr(a, np.uint16, n_a * BITS, "a"), n_a, _ptr(b, np.uint16, n_b * BITS, "b"), n_b,
+                                    _ptr(out, np.uint16, n_a * n_b, "out")))
+    return out
+
+
+def dot_bool_batch(a, b, out=None, device: int = 0):
+    """The criterion grid for dot_bool (src/arch/mod.rs:22-44): a = [n_a][200] u64, b = [n_b][200] u64 or a Database."""
+    n_a = _numel(a) // LIMBS
+    if isinstance(b, Database):
+        n_b = b.len_masks
+        out = np.empty((n_b, n_a), np.uint16) if out is None else out
+        _check(lib().iris_dot_bool_batch_resident(_ptr(a, np.uint64, n_a * LIMBS, "a"), n_a, b._h, 0, n_b, _ptr(out, np.uint16, n_a * n_b, "out")))
+        return out
+    n_b = _numel(b) // LIMBS
+    out = np.empty((n_b, n_a), np.uint16) if out is None else out
+    _check(lib().iris_dot_bool_batch(device, _ptr(a, np.uint64, n_a * LIMBS, "a"), n_a, _ptr(b, np.uint64, n_b * LIMBS, "b"), n_b,
+                                     _ptr(out, np.uint16, n_a * n_b, "out")))
+    return out
+
+
 # ------------------------------------------------------------------ database shard
 class Database:
     """HBM-resident shard: the reference's mmapped &[EncodedBits] / &[Bits] (src/main.rs:389-391, 458-461)."""
 
-    def __init__(self, capacity_rows: int, device: int = 0, shares: bool = True, masks: bool = True):
+    def __init__(self, capacity_rows: int, device: int = 0, shares: bool = True, masks: bool = True, _borrowed=None):
         self._h = ctypes.c_void_p()
         self.device = device
+        self._owned = _borrowed is None
+        if _borrowed is not None:          # a shard of a Cluster: the cluster owns it
+            self._h = _borrowed
+            return
         flags = (IRIS_DB_SHARES if shares else 0) | (IRIS_DB_MASKS if masks else 0)
         _check(lib().iris_db_create(device, capacity_rows, flags, ctypes.byref(self._h)))
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
-            lib().iris_db_destroy(self._h)
+            if self._owned:
+                lib().iris_db_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):
@@ -234,6 +296,19 @@ class Database:
 
     def generate(self, seed: int, first_row_id: int, n: int) -> None:
         _check(lib().iris_db_generate(self._h, seed, first_row_id, n))
+
+    def generate_shares(self, seed: int, party: int, n_parties: int, first_row_id: int, n: int) -> None:
+        """Party `party`'s additive shares (EncodedBits::share, src/encoded_bits.rs:23-38) of the encodings of the
+        synthetic Templates with row ids first_row_id..; n_parties = 1 stores the plaintext encodings."""
+        _check(lib().iris_db_generate_shares(self._h, seed, party, n_parties, first_row_id, n))
+
+    def write_shares(self, row: int, rows) -> None:
+        n = _numel(rows) // BITS
+        _check(lib().iris_db_write_shares(self._h, row, _ptr(rows, np.uint16, n * BITS, "rows"), n))
+
+    def write_masks(self, row: int, rows) -> None:
+        n = _numel(rows) // LIMBS
+        _check(lib().iris_db_write_masks(self._h, row, _ptr(rows, np.uint64, n * LIMBS, "rows"), n))
 
     def read_shares(self, row_begin: int, n: int) -> np.ndarray:
         out = np.empty((n, BITS), np.uint16)
@@ -464,3 +539,96 @@ def denominators(query, entry, device: int = 0) -> np.ndarray:
     out = np.zeros(ROTATIONS, np.uint16)
     _check(lib().iris_denominators(device, _ptr(query, np.uint64, LIMBS, "query"), _ptr(entry, np.uint64, LIMBS, "entry"), out.ctypes.data))
     return out
+
+
+# ------------------------------------------------------------------ cluster: one database over several GPUs
+def cluster_partition(n_total: int, n_shards: int, shard: int):
+    b, e = ctypes.c_uint64(), ctypes.c_uint64()
+    _check(lib().iris_cluster_partition(n_total, n_shards, shard, ctypes.byref(b), ctypes.byref(e)))
+    return b.value, e.value
+
+
+def comm_unique_id() -> bytes:
+    """The id rank 0 draws for a multi-process cluster (128 bytes; hand it to the other processes by any channel)."""
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().iris_comm_unique_id(buf))
+    return buf.raw
+
+
+class Cluster:
+    """One database row-sharded over `devices` (the compiled library runs one host thread + stream per GPU).
+    search() gathers 16 bytes per query and shard over NVLink; match() lets every GPU store its block of the
+    [n][31] results into one array (on any GPU of the cluster, or in host memory)."""
+
+    def __init__(self, devices, capacity_rows: int, shares: bool = True, masks: bool = True):
+        self._h = ctypes.c_void_p()
+        self.devices = list(devices)
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        flags = (IRIS_DB_SHARES if shares else 0) | (IRIS_DB_MASKS if masks else 0)
+        _check(lib().iris_cluster_create(arr, len(self.devices), capacity_rows, flags, ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().iris_cluster_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self) -> int:
+        ns, a, b = ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_uint64()
+        _check(lib().iris_cluster_len(self._h, ctypes.byref(ns), ctypes.byref(a), ctypes.byref(b)))
+        return max(a.value, b.value)
+
+    def shard(self, i: int):
+        """(Database view, device, row_begin, row_end) of shard i."""
+        h, dev, b, e = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_uint64(), ctypes.c_uint64()
+        _check(lib().iris_cluster_shard(self._h, i, ctypes.byref(h), ctypes.byref(dev), ctypes.byref(b), ctypes.byref(e)))
+        return Database(0, dev.value, _borrowed=h), dev.value, b.value, e.value
+
+    def generate(self, seed: int, n: int, first_row_id: int = 0, party: int = 0, n_parties: int = 1) -> None:
+        _check(lib().iris_cluster_generate(self._h, seed, party, n_parties, first_row_id, n))
+
+    def load_files(self, shares_path: Optional[str], masks_path: Optional[str]) -> None:
+        _check(lib().iris_cluster_load_files(self._h, os.fsencode(shares_path) if shares_path else None,
+                                             os.fsencode(masks_path) if masks_path else None))
+
+    def load_rows(self, shares=None, masks=None) -> None:
+        n = _numel(shares) // BITS if shares is not None else _numel(masks) // LIMBS
+        _check(lib().iris_cluster_load_rows(self._h, _ptr(shares, np.uint16, n * BITS, "shares"),
+                                            _ptr(masks, np.uint64, n * LIMBS, "masks"), n))
+
+    def set_index_base(self, base: int) -> None:
+        _check(lib().iris_cluster_set_index_base(self._h, base))
+
+    def join(self, unique_id: bytes, rank: int, world_size: int) -> None:
+        _check(lib().iris_cluster_join(self._h, unique_id, rank, world_size))
+
+    def match(self, query=None, query_mask=None, distances_out=None, denominators_out=None) -> None:
+        n = len(self) * ROTATIONS
+        _check(lib().iris_cluster_match(self._h, _ptr(query, np.uint16, BITS, "query"), _ptr(query_mask, np.uint64, LIMBS, "query_mask"),
+                                        _ptr(distances_out, np.uint16, n, "distances_out"),
+                                        _ptr(denominators_out, np.uint16, n, "denominators_out")))
+
+    def match_template(self, pattern, mask, distances_out, denominators_out=None) -> None:
+        n = len(self) * ROTATIONS
+        _check(lib().iris_cluster_match_template(self._h, _ptr(pattern, np.uint64, LIMBS, "pattern"), _ptr(mask, np.uint64, LIMBS, "mask"),
+                                                 _ptr(distances_out, np.uint16, n, "distances_out"),
+                                                 _ptr(denominators_out, np.uint16, n, "denominators_out")))
+
+    def search(self, templates):
+        """templates: [Q][400] u64 wire Templates -> (min distances [Q] f64, rows [Q] i64, -1 = none)."""
+        q = _numel(templates) // (2 * LIMBS)
+        md = (ctypes.c_double * q)()
+        mi = (ctypes.c_uint64 * q)()
+        _check(lib().iris_cluster_search(self._h, _ptr(templates, np.uint64, q * 2 * LIMBS, "templates"), q, md, mi))
+        return np.array(md[:], np.float64), np.array([-1 if v == 2**64 - 1 else v for v in mi[:]], np.int64)

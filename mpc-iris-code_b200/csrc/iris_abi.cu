@@ -97,6 +97,10 @@ struct iris_db {
     uint64_t res_rows = 0;
     uint8_t* d_red = nullptr;        // match_min: results + reduction scratch
     uint64_t red_rows = 0;
+    uint8_t* d_batch = nullptr;      // batched search: [Q][slice][31] distances + denominators + reduction scratch
+    size_t batch_bytes = 0;
+    ResultPair* d_pairs = nullptr;   // per-slice result pairs of a search
+    size_t pairs_cap = 0;
     // Watchdog flag: mapped page-locked HOST memory, so the code a trapping kernel leaves behind can still be read
     // after the trap has poisoned the context.  h_error is the host view, d_error the device alias.
     int* h_error = nullptr;
@@ -368,6 +372,8 @@ extern "C" int iris_db_destroy(iris_db* db) {
     cudaFree(db->d_masks);
     cudaFree(db->d_stage);
     cudaFree(db->d_red);
+    cudaFree(db->d_batch);
+    cudaFree(db->d_pairs);
     if (db->h_error) cudaFreeHost(db->h_error);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 2; ++k) cudaFree(db->d_res[b][k]);
@@ -484,24 +490,48 @@ static int ensure_stage(iris_db* db) {
     return IRIS_OK;
 }
 
-extern "C" int iris_db_append_shares(iris_db* db, const uint16_t* rows, uint64_t n) {
-    if (!db || (!rows && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
-    if (!(db->flags & IRIS_DB_SHARES)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_SHARES");
-    if (db->n_shares + n > db->capacity)
-        return fail(IRIS_ERR_INVALID, "append of %llu rows exceeds capacity %llu", (unsigned long long)n, (unsigned long long)db->capacity);
+// rows (reference layout; host, or device after the producing stream has been synchronised by the caller) ->
+// tiled image at rows [row0, row0 + n)
+static int upload_shares(iris_db* db, const uint16_t* rows, uint64_t n, uint64_t row0) {
     DeviceGuard g(db->device);
     if (is_device_pointer(rows)) {
-        CK(launch_retile_shares(rows, n, db->d_shares, db->n_shares, db->stream));
+        CK(launch_retile_shares(rows, n, db->d_shares, row0, db->stream));
     } else {
         int rc = ensure_stage(db);
         if (rc) return rc;
         for (uint64_t off = 0; off < n; off += kStageRows) {
             const uint64_t m = std::min(kStageRows, n - off);
             CK(cudaMemcpyAsync(db->d_stage, rows + off * IRIS_BITS, m * IRIS_BITS * sizeof(uint16_t), cudaMemcpyHostToDevice, db->stream));
-            CK(launch_retile_shares(static_cast<const uint16_t*>(db->d_stage), m, db->d_shares, db->n_shares + off, db->stream));
+            CK(launch_retile_shares(static_cast<const uint16_t*>(db->d_stage), m, db->d_shares, row0 + off, db->stream));
         }
     }
-    CK(cudaStreamSynchronize(db->stream));
+    return sync_checked(db, db->stream);
+}
+
+static int upload_masks(iris_db* db, const uint64_t* rows, uint64_t n, uint64_t row0) {
+    DeviceGuard g(db->device);
+    if (is_device_pointer(rows)) {
+        CK(launch_retile_masks(reinterpret_cast<const uint8_t*>(rows), n, db->d_masks, row0, db->stream));
+    } else {
+        int rc = ensure_stage(db);
+        if (rc) return rc;
+        const uint64_t step = kStageRows * 16;   // same staging buffer, 1600-byte rows
+        for (uint64_t off = 0; off < n; off += step) {
+            const uint64_t m = std::min(step, n - off);
+            CK(cudaMemcpyAsync(db->d_stage, rows + off * IRIS_LIMBS, m * IRIS_MASK_BYTES, cudaMemcpyHostToDevice, db->stream));
+            CK(launch_retile_masks(static_cast<const uint8_t*>(db->d_stage), m, db->d_masks, row0 + off, db->stream));
+        }
+    }
+    return sync_checked(db, db->stream);
+}
+
+extern "C" int iris_db_append_shares(iris_db* db, const uint16_t* rows, uint64_t n) {
+    if (!db || (!rows && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_SHARES)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_SHARES");
+    if (db->n_shares + n > db->capacity)
+        return fail(IRIS_ERR_INVALID, "append of %llu rows exceeds capacity %llu", (unsigned long long)n, (unsigned long long)db->capacity);
+    int rc = upload_shares(db, rows, n, db->n_shares);
+    if (rc) return rc;
     db->n_shares += n;
     return IRIS_OK;
 }
@@ -511,22 +541,25 @@ extern "C" int iris_db_append_masks(iris_db* db, const uint64_t* rows, uint64_t 
     if (!(db->flags & IRIS_DB_MASKS)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_MASKS");
     if (db->n_masks + n > db->capacity)
         return fail(IRIS_ERR_INVALID, "append of %llu rows exceeds capacity %llu", (unsigned long long)n, (unsigned long long)db->capacity);
-    DeviceGuard g(db->device);
-    if (is_device_pointer(rows)) {
-        CK(launch_retile_masks(reinterpret_cast<const uint8_t*>(rows), n, db->d_masks, db->n_masks, db->stream));
-    } else {
-        int rc = ensure_stage(db);
-        if (rc) return rc;
-        const uint64_t step = kStageRows * 16;   // same staging buffer, 1600-byte rows
-        for (uint64_t off = 0; off < n; off += step) {
-            const uint64_t m = std::min(step, n - off);
-            CK(cudaMemcpyAsync(db->d_stage, rows + off * IRIS_LIMBS, m * IRIS_MASK_BYTES, cudaMemcpyHostToDevice, db->stream));
-            CK(launch_retile_masks(static_cast<const uint8_t*>(db->d_stage), m, db->d_masks, db->n_masks + off, db->stream));
-        }
-    }
-    CK(cudaStreamSynchronize(db->stream));
+    int rc = upload_masks(db, rows, n, db->n_masks);
+    if (rc) return rc;
     db->n_masks += n;
     return IRIS_OK;
+}
+
+// Overwrite rows that are already loaded (an enrolment update; the tests and the bench plant known templates).
+extern "C" int iris_db_write_shares(iris_db* db, uint64_t row, const uint16_t* rows, uint64_t n) {
+    if (!db || (!rows && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_SHARES)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_SHARES");
+    if (row + n > db->n_shares) return fail(IRIS_ERR_INVALID, "rows [%llu,%llu) beyond the %llu loaded shares", (unsigned long long)row, (unsigned long long)(row + n), (unsigned long long)db->n_shares);
+    return upload_shares(db, rows, n, row);
+}
+
+extern "C" int iris_db_write_masks(iris_db* db, uint64_t row, const uint64_t* rows, uint64_t n) {
+    if (!db || (!rows && n)) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (!(db->flags & IRIS_DB_MASKS)) return fail(IRIS_ERR_STATE, "shard was created without IRIS_DB_MASKS");
+    if (row + n > db->n_masks) return fail(IRIS_ERR_INVALID, "rows [%llu,%llu) beyond the %llu loaded masks", (unsigned long long)row, (unsigned long long)(row + n), (unsigned long long)db->n_masks);
+    return upload_masks(db, rows, n, row);
 }
 
 extern "C" int iris_db_generate(iris_db* db, uint64_t seed, uint64_t first_row_id, uint64_t n) {
@@ -543,6 +576,28 @@ extern "C" int iris_db_generate(iris_db* db, uint64_t seed, uint64_t first_row_i
         CK(launch_generate(s ? db->d_shares : nullptr, m ? db->d_masks : nullptr, seed, first_row_id + off, row0 + off, cnt, db->stream));
     }
     CK(cudaStreamSynchronize(db->stream));
+    if (s) db->n_shares += n;
+    if (m) db->n_masks += n;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_generate_shares(iris_db* db, uint64_t seed, uint32_t party, uint32_t n_parties, uint64_t first_row_id,
+                                       uint64_t n) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    if (n_parties == 0 || party >= n_parties) return fail(IRIS_ERR_INVALID, "party %u of %u", party, n_parties);
+    const bool s = db->flags & IRIS_DB_SHARES, m = db->flags & IRIS_DB_MASKS;
+    if (s && m && db->n_shares != db->n_masks) return fail(IRIS_ERR_STATE, "shares and masks lengths differ");
+    const uint64_t row0 = s ? db->n_shares : db->n_masks;
+    if (row0 + n > db->capacity) return fail(IRIS_ERR_INVALID, "generate exceeds capacity");
+    DeviceGuard g(db->device);
+    const uint64_t step = 1u << 18;     // bounded launches (grid dimension limits)
+    for (uint64_t off = 0; off < n; off += step) {
+        const uint64_t cnt = std::min(step, n - off);
+        if (s) CK(launch_generate_party_shares(db->d_shares, seed, party, n_parties, first_row_id + off, row0 + off, cnt, db->stream));
+        if (m) CK(launch_generate(nullptr, db->d_masks, seed, first_row_id + off, row0 + off, cnt, db->stream));
+    }
+    int rc = sync_checked(db, db->stream);
+    if (rc) return rc;
     if (s) db->n_shares += n;
     if (m) db->n_masks += n;
     return IRIS_OK;
@@ -1481,20 +1536,19 @@ extern "C" int iris_combine_min_batch(int device, const uint16_t* distances, con
     if (!is_device_pointer(distances) || !is_device_pointer(denominators))
         return fail(IRIS_ERR_INVALID, "iris_combine_min_batch takes device arrays");
     DeviceGuard g(device);
-    const size_t sbytes = (combine_scratch_bytes(n) + 15) / 16 * 16;
+    const size_t sbytes = ((size_t)num_queries * combine_scratch_bytes(n) + 15) / 16 * 16;
     uint8_t* scratch = nullptr;
     rc = temp_alloc(device, reinterpret_cast<void**>(&scratch), sbytes + 16 * (size_t)num_queries);
     if (rc) return rc;
     auto body = [&]() -> int {
-        for (uint32_t q = 0; q < num_queries; ++q) {
-            CombineParams p{};
-            p.shares[0] = distances + (size_t)q * n * IRIS_ROTATIONS;
-            p.parties = 1;
-            p.denominators = denominators + (size_t)q * n * IRIS_ROTATIONS;
-            p.n = n;
-            p.index_base = index_base;
-            CK(launch_combine_min(p, scratch, scratch + sbytes + 16 * (size_t)q, cudaStreamPerThread));
-        }
+        CombineParams p{};
+        p.shares[0] = distances;
+        p.parties = 1;
+        p.denominators = denominators;
+        p.n = n;
+        p.index_base = index_base;
+        p.query_stride = (size_t)n * IRIS_ROTATIONS;
+        CK(launch_combine_min(p, scratch, scratch + sbytes, cudaStreamPerThread, num_queries));
         std::vector<uint64_t> host(2 * (size_t)num_queries);
         CK(cudaMemcpyAsync(host.data(), scratch + sbytes, 16 * (size_t)num_queries, cudaMemcpyDeviceToHost, cudaStreamPerThread));
         CK(cudaStreamSynchronize(cudaStreamPerThread));
@@ -1512,13 +1566,16 @@ extern "C" int iris_combine_min_batch(int device, const uint16_t* distances, con
 
 // Fused scan + reduction on a resident shard holding the full (n = 1 share) encodings: both engines over
 // rows [row_begin,row_end), then decode + min/argmin on the device; only 16 bytes come back.
-extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
-                                       uint64_t row_end, uint64_t index_base, double* min_distance, uint64_t* min_index) {
-    if (!de || !me || !db || !min_distance || !min_index) return fail(IRIS_ERR_INVALID, "NULL argument");
+// Asynchronous core: the pair is written to `result` -- device memory of this or (with peer access enabled) another
+// GPU, or mapped host memory -- in stream order on the shard's stream.  No host synchronisation.
+extern "C" int iris_match_min_resident_async(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
+                                             uint64_t row_end, uint64_t index_base, void* result) {
+    if (!de || !me || !db || !result) return fail(IRIS_ERR_INVALID, "NULL argument");
     if (row_end < row_begin) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
     DeviceGuard g(db->device);
     const uint64_t n = row_end - row_begin;
-    if (db->red_rows < n) {
+    if (db->red_rows < n || !db->d_red) {
+        CK(cudaStreamSynchronize(db->stream));           // an earlier asynchronous search may still use the buffer
         cudaFree(db->d_red);
         db->d_red = nullptr;
         db->red_rows = 0;
@@ -1526,11 +1583,10 @@ extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engi
         CK(cudaMalloc(&db->d_red, 2 * row_bytes + combine_scratch_bytes(n) + 64));
         db->red_rows = n;
     }
-    const size_t row_bytes = (n * kOutRowBytes + 63) / 64 * 64;
+    const size_t row_bytes = (db->red_rows * kOutRowBytes + 63) / 64 * 64;
     uint16_t* d_dist = reinterpret_cast<uint16_t*>(db->d_red);
     uint16_t* d_den = reinterpret_cast<uint16_t*>(db->d_red + row_bytes);
     uint8_t* scratch = db->d_red + 2 * row_bytes;
-    void* result = scratch + (combine_scratch_bytes(n) / 16) * 16 + 16;
     if (n) {
         int rc = scan_core(db, de, me, row_begin, row_end, d_dist, d_den, nullptr);
         if (rc) return rc;
@@ -1542,14 +1598,275 @@ extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engi
     p.n = n;
     p.index_base = index_base + row_begin;
     CK(launch_combine_min(p, scratch, result, db->stream));
-    struct { double v; unsigned long long i; } h;
-    CK(cudaMemcpyAsync(&h, result, sizeof h, cudaMemcpyDeviceToHost, db->stream));
-    CK(cudaStreamSynchronize(db->stream));
-    int rc = check_error_flag(db);
-    if (rc) return rc;
-    *min_distance = h.v;
-    *min_index = h.i;
     return IRIS_OK;
+}
+
+static int ensure_pairs(iris_db* db, size_t n_pairs) {
+    if (db->pairs_cap >= n_pairs) return IRIS_OK;
+    CK(cudaStreamSynchronize(db->stream));
+    cudaFree(db->d_pairs);
+    db->d_pairs = nullptr;
+    db->pairs_cap = 0;
+    CK(cudaMalloc(reinterpret_cast<void**>(&db->d_pairs), n_pairs * sizeof(ResultPair)));
+    db->pairs_cap = n_pairs;
+    return IRIS_OK;
+}
+
+extern "C" int iris_match_min_resident(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
+                                       uint64_t row_end, uint64_t index_base, double* min_distance, uint64_t* min_index) {
+    if (!de || !me || !db || !min_distance || !min_index) return fail(IRIS_ERR_INVALID, "NULL argument");
+    DeviceGuard g(db->device);
+    int rc = ensure_pairs(db, 64);
+    if (rc) return rc;
+    rc = iris_match_min_resident_async(de, me, db, row_begin, row_end, index_base, db->d_pairs);
+    if (rc) return rc;
+    ResultPair h;
+    CK(cudaMemcpyAsync(&h, db->d_pairs, sizeof h, cudaMemcpyDeviceToHost, db->stream));
+    rc = sync_checked(db, db->stream);
+    if (rc) return rc;
+    rc = check_error_flag(db);
+    if (rc) return rc;
+    *min_distance = h.min_distance;
+    *min_index = h.min_index;
+    return IRIS_OK;
+}
+
+// Batched search on one shard (BASELINE configs[3]/[4] per GPU): num_queries engine pairs against rows
+// [row_begin,row_end) -- batched tensor-core distances and denominators slice by slice into scratch arrays owned by
+// the shard, decode + min/argmin per query and slice on the device, running min over the slices -- and the
+// num_queries result pairs written to `results` (device / peer / mapped host memory) in stream order.
+static constexpr uint64_t kSearchSliceElems = 1ull << 25;        // rows x queries per slice: 2 x 2.08 GB of scratch
+extern "C" int iris_search_batch_resident_async(iris_distance_engine* const* des, iris_masks_engine* const* mes,
+                                                uint32_t num_queries, iris_db* db, uint64_t row_begin, uint64_t row_end,
+                                                uint64_t index_base, void* results) {
+    if (!des || !mes || !db || !results) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (num_queries == 0) return IRIS_OK;
+    if (num_queries > (uint32_t)kMaxBatchQueries) return fail(IRIS_ERR_INVALID, "at most %d queries per search", kMaxBatchQueries);
+    if (row_end < row_begin) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    DeviceGuard g(db->device);
+    const uint64_t n = row_end - row_begin;
+    const uint64_t slice = std::max<uint64_t>(2 * kTileRows, kSearchSliceElems / num_queries / (2 * kTileRows) * (2 * kTileRows));
+    const uint64_t srows = std::min(n, slice);
+    const uint32_t n_slices = (uint32_t)std::max<uint64_t>(1, (n + slice - 1) / slice);
+    const size_t arr_bytes = ((size_t)num_queries * srows * kOutRowBytes + 255) / 256 * 256;
+    const size_t scratch_bytes = ((size_t)num_queries * combine_scratch_bytes(srows) + 255) / 256 * 256;
+    const size_t need = 2 * arr_bytes + scratch_bytes + 256;
+    if (db->batch_bytes < need) {
+        CK(cudaStreamSynchronize(db->stream));
+        cudaFree(db->d_batch);
+        db->d_batch = nullptr;
+        db->batch_bytes = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&db->d_batch), need));
+        db->batch_bytes = need;
+    }
+    int rc = ensure_pairs(db, (size_t)n_slices * num_queries);
+    if (rc) return rc;
+    uint16_t* d_bd = reinterpret_cast<uint16_t*>(db->d_batch);
+    uint16_t* d_bn = reinterpret_cast<uint16_t*>(db->d_batch + arr_bytes);
+    uint8_t* scratch = db->d_batch + 2 * arr_bytes;
+    for (uint32_t sidx = 0; sidx < n_slices; ++sidx) {
+        const uint64_t b = row_begin + (uint64_t)sidx * slice, e = std::min(row_end, b + slice);
+        CombineParams p{};
+        p.shares[0] = d_bd;
+        p.parties = 1;
+        p.denominators = d_bn;
+        p.n = e - b;
+        p.index_base = index_base + b;
+        p.query_stride = (size_t)(e - b) * IRIS_ROTATIONS;
+        if (e > b) {
+            rc = iris_distances_batch_resident(des, num_queries, db, b, e, d_bd);
+            if (rc) return rc;
+            rc = iris_denominators_batch_resident(mes, num_queries, db, b, e, d_bn);
+            if (rc) return rc;
+        }
+        CK(launch_combine_min(p, scratch, db->d_pairs + (size_t)sidx * num_queries, db->stream, num_queries));
+    }
+    CK(launch_merge_pairs(db->d_pairs, n_slices, num_queries, num_queries, static_cast<ResultPair*>(results), db->stream));
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_get_stream(iris_db* db, void** cuda_stream) {
+    if (!db || !cuda_stream) return fail(IRIS_ERR_INVALID, "NULL argument");
+    *cuda_stream = db->stream;
+    return IRIS_OK;
+}
+
+extern "C" int iris_db_device(const iris_db* db, int* device) {
+    if (!db || !device) return fail(IRIS_ERR_INVALID, "NULL argument");
+    *device = db->device;
+    return IRIS_OK;
+}
+
+// Watchdog state of a shard after the caller has synchronised its stream itself.
+extern "C" int iris_db_check(iris_db* db) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    return check_error_flag(db);
+}
+
+namespace iris {
+void set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
+}
+
+// ------------------------------------------------------------------------------------ arch-level batched dots
+// The reference's criterion grid (src/arch/mod.rs:22-72) calls dot_u16 / dot_bool on every pair of `a` independent
+// vectors and `b` database vectors.  Up to 31 vectors take the slots of the 31 rotations of one "engine"
+// (iris_dotbatch.cu), so the same scan / batched-GEMM kernels compute out[i][j] = dot(a[j], b[i]).
+static int vectors_to_device(int device, const void* a, size_t bytes, cudaStream_t s, uint8_t** d_out) {
+    int rc = temp_alloc(device, reinterpret_cast<void**>(d_out), bytes, s);
+    if (rc) return rc;
+    if (is_device_pointer(a)) {
+        CK(cudaMemcpyAsync(*d_out, a, bytes, cudaMemcpyDeviceToDevice, s));
+    } else {
+        ThreadStage* st = nullptr;
+        rc = thread_stage(device, bytes, &st);
+        if (rc) return rc;
+        std::memcpy(st->p, a, bytes);
+        CK(cudaMemcpyAsync(*d_out, st->p, bytes, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(st->done, s));
+    }
+    return IRIS_OK;
+}
+
+static int distance_engines_from_vectors(int device, const uint16_t* a, uint32_t n_vec, std::vector<iris_distance_engine*>& out) {
+    cudaStream_t s = cudaStreamPerThread;
+    uint8_t* d_a = nullptr;
+    int rc = vectors_to_device(device, a, (size_t)n_vec * IRIS_BITS * 2, s, &d_a);
+    if (rc) {
+        temp_free(d_a, s);
+        return rc;
+    }
+    auto body = [&]() -> int {
+        for (uint32_t v0 = 0; v0 < n_vec; v0 += IRIS_ROTATIONS) {
+            iris_distance_engine* e = nullptr;
+            int r = new_distance_engine(device, s, &e);
+            if (r) return r;
+            out.push_back(e);
+            int* h_flag = reinterpret_cast<int*>(e->slot.h + IRIS_BITS * 2);
+            int* d_flag = nullptr;
+            *h_flag = 1;
+            CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_flag), h_flag, 0));
+            CK(launch_prep_distance_vectors(reinterpret_cast<const uint16_t*>(d_a) + (size_t)v0 * IRIS_BITS,
+                                            std::min<uint32_t>(IRIS_ROTATIONS, n_vec - v0), e->d_qd, d_flag, s));
+            CK(cudaEventRecord(e->slot.ready, s));
+            e->classified = false;
+        }
+        return IRIS_OK;
+    };
+    rc = body();
+    temp_free(d_a, s);
+    return rc;
+}
+
+static int masks_engines_from_vectors(int device, const uint64_t* a, uint32_t n_vec, std::vector<iris_masks_engine*>& out) {
+    cudaStream_t s = cudaStreamPerThread;
+    uint8_t* d_a = nullptr;
+    int rc = vectors_to_device(device, a, (size_t)n_vec * IRIS_MASK_BYTES, s, &d_a);
+    if (rc) {
+        temp_free(d_a, s);
+        return rc;
+    }
+    auto body = [&]() -> int {
+        for (uint32_t v0 = 0; v0 < n_vec; v0 += IRIS_ROTATIONS) {
+            iris_masks_engine* e = nullptr;
+            int r = new_masks_engine(device, s, &e);
+            if (r) return r;
+            out.push_back(e);
+            CK(launch_prep_mask_vectors(d_a + (size_t)v0 * IRIS_MASK_BYTES, std::min<uint32_t>(IRIS_ROTATIONS, n_vec - v0), e->d_qm,
+                                        e->d_qm + kQmBytes, s));
+            CK(cudaEventRecord(e->slot.ready, s));
+        }
+        return IRIS_OK;
+    };
+    rc = body();
+    temp_free(d_a, s);
+    return rc;
+}
+
+template <bool U16>
+static int dot_batch_resident(const void* a, uint32_t n_a, iris_db* db, uint64_t row_begin, uint64_t row_end, uint16_t* out) {
+    if (!a || !db) return fail(IRIS_ERR_INVALID, "NULL argument");
+    if (row_begin > row_end) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    if (n_a == 0 || row_begin == row_end) return IRIS_OK;
+    if (!out) return fail(IRIS_ERR_INVALID, "out is NULL");
+    if (n_a > 31u * kMaxBatchQueries) return fail(IRIS_ERR_INVALID, "at most %u vectors per call", 31u * kMaxBatchQueries);
+    DeviceGuard g(db->device);
+    const uint64_t n = row_end - row_begin;
+    const uint32_t groups = (n_a + IRIS_ROTATIONS - 1) / IRIS_ROTATIONS;
+    std::vector<iris_distance_engine*> des;
+    std::vector<iris_masks_engine*> mes;
+    int rc = U16 ? distance_engines_from_vectors(db->device, static_cast<const uint16_t*>(a), n_a, des)
+                 : masks_engines_from_vectors(db->device, static_cast<const uint64_t*>(a), n_a, mes);
+    uint16_t* d_tmp = nullptr;
+    uint16_t* d_res = nullptr;
+    const bool out_dev = is_device_pointer(out);
+    auto body = [&]() -> int {
+        if (rc) return rc;
+        // [groups][n][31] intermediate, unless the caller's array already has that shape (31 vectors, device memory)
+        const bool direct = n_a == IRIS_ROTATIONS && out_dev;
+        if (!direct) {
+            int r = temp_alloc(db->device, reinterpret_cast<void**>(&d_tmp), (size_t)groups * n * kOutRowBytes + 64, db->stream);
+            if (r) return r;
+        }
+        uint16_t* grid = direct ? out : d_tmp;
+        int r = U16 ? iris_distances_batch_resident(des.data(), groups, db, row_begin, row_end, grid)
+                    : iris_denominators_batch_resident(mes.data(), groups, db, row_begin, row_end, grid);
+        if (r) return r;
+        if (direct) return IRIS_OK;
+        uint16_t* dst = out;
+        if (!out_dev) {
+            r = temp_alloc(db->device, reinterpret_cast<void**>(&d_res), (size_t)n * n_a * 2 + 64, db->stream);
+            if (r) return r;
+            dst = d_res;
+        }
+        CK(launch_compact_columns(d_tmp, n, n_a, dst, db->stream));
+        if (!out_dev) {
+            CK(cudaMemcpyAsync(out, d_res, (size_t)n * n_a * 2, cudaMemcpyDeviceToHost, db->stream));
+            int r2 = sync_checked(db, db->stream);
+            if (r2) return r2;
+            return check_error_flag(db);
+        }
+        return IRIS_OK;
+    };
+    rc = body();
+    std::string keep = g_last_error;
+    temp_free(d_tmp, db->stream);
+    temp_free(d_res, db->stream);
+    for (auto* e : des) iris_distance_engine_free(e);
+    for (auto* e : mes) iris_masks_engine_free(e);
+    g_last_error = keep;
+    return rc;
+}
+
+extern "C" int iris_dot_u16_batch_resident(const uint16_t* a, uint32_t n_a, iris_db* db, uint64_t row_begin,
+                                           uint64_t row_end, uint16_t* out) {
+    return dot_batch_resident<true>(a, n_a, db, row_begin, row_end, out);
+}
+extern "C" int iris_dot_bool_batch_resident(const uint64_t* a, uint32_t n_a, iris_db* db, uint64_t row_begin,
+                                            uint64_t row_end, uint16_t* out) {
+    return dot_batch_resident<false>(a, n_a, db, row_begin, row_end, out);
+}
+
+// Host-array forms: `b` is uploaded into a temporary shard first (PCIe-bound; for throughput keep the vectors resident).
+template <bool U16>
+static int dot_batch_host(int device, const void* a, uint32_t n_a, const void* b, uint64_t n_b, uint16_t* out) {
+    if (!a || !b || !out) return (n_a == 0 || n_b == 0) ? IRIS_OK : fail(IRIS_ERR_INVALID, "NULL argument");
+    if (n_a == 0 || n_b == 0) return IRIS_OK;
+    iris_db* db = nullptr;
+    int rc = iris_db_create(device, n_b, U16 ? IRIS_DB_SHARES : IRIS_DB_MASKS, &db);
+    if (rc) return rc;
+    rc = U16 ? iris_db_append_shares(db, static_cast<const uint16_t*>(b), n_b) : iris_db_append_masks(db, static_cast<const uint64_t*>(b), n_b);
+    if (!rc) rc = dot_batch_resident<U16>(a, n_a, db, 0, n_b, out);
+    if (!rc) rc = iris_db_synchronize(db);
+    std::string keep = g_last_error;
+    iris_db_destroy(db);
+    g_last_error = keep;
+    return rc;
+}
+extern "C" int iris_dot_u16_batch(int device, const uint16_t* a, uint32_t n_a, const uint16_t* b, uint64_t n_b, uint16_t* out) {
+    return dot_batch_host<true>(device, a, n_a, b, n_b, out);
+}
+extern "C" int iris_dot_bool_batch(int device, const uint64_t* a, uint32_t n_a, const uint64_t* b, uint64_t n_b, uint16_t* out) {
+    return dot_batch_host<false>(device, a, n_a, b, n_b, out);
 }
 
 // ------------------------------------------------------------------------------------ per-pair arch entry points

@@ -600,7 +600,7 @@ __global__ void generate_shares_kernel(uint8_t* __restrict__ shares, uint64_t se
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const uint64_t g = (uint64_t)g16 * 4 + t;
-        const uint64_t h = mix64(seed ^ (((row_id0 + i) * (IRIS_BITS / 4) + g) * 0xD1342543DE82EF95ull));
+        const uint64_t h = gen_share_group(seed, row_id0 + i, g);
         const uint32_t x = (uint32_t)h, y = (uint32_t)(h >> 32);
         lo[t] = __byte_perm(x, y, 0x6420);
         hi[t] = __byte_perm(x, y, 0x7531);
@@ -616,11 +616,71 @@ __global__ void generate_masks_kernel(uint8_t* __restrict__ masks, uint64_t seed
     if (idx >= n * kChunks) return;
     const uint64_t i = idx / kChunks;
     const uint32_t c = (uint32_t)(idx % kChunks);
-    const uint64_t s2 = seed ^ 0xA5A5A5A55A5A5A5Aull;
-    const uint64_t h0 = mix64(s2 ^ (((row_id0 + i) * IRIS_LIMBS + 2 * c) * 0xD1342543DE82EF95ull));
-    const uint64_t h1 = mix64(s2 ^ (((row_id0 + i) * IRIS_LIMBS + 2 * c + 1) * 0xD1342543DE82EF95ull));
+    const uint64_t h0 = gen_bits_limb(seed, kGenMaskTag, row_id0 + i, 2 * c);
+    const uint64_t h1 = gen_bits_limb(seed, kGenMaskTag, row_id0 + i, 2 * c + 1);
     *reinterpret_cast<uint4*>(masks + mask_offset(row0 + i, c * 16)) =
         make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
+}
+
+// Party `party`'s additive share of encode(Template R) (see iris_kernels.cuh): uniform for every party but the last,
+// which holds the encoding minus the sum of the others (src/encoded_bits.rs:23-38).
+__global__ void generate_party_shares_kernel(uint8_t* __restrict__ shares, uint64_t seed, uint32_t party, uint32_t n_parties,
+                                             uint64_t row_id0, uint64_t row0, uint64_t n) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row i, group of 16 elements)
+    if (idx >= n * (IRIS_BITS / 16)) return;
+    const uint64_t i = idx / (IRIS_BITS / 16);
+    const uint32_t g16 = (uint32_t)(idx % (IRIS_BITS / 16));
+    const uint64_t R = row_id0 + i;
+    uint32_t w[8];                                   // 16 u16 elements, two per word
+    if (party + 1 < n_parties) {
+        const uint64_t ps = gen_party_seed(seed, party);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint64_t h = gen_share_group(ps, R, (uint64_t)g16 * 4 + t);
+            w[2 * t] = (uint32_t)h;
+            w[2 * t + 1] = (uint32_t)(h >> 32);
+        }
+    } else {
+        // encode (src/lib.rs:16-26): mask - 2 (pattern & mask) -> 1, 0, 0xFFFF; 16 elements = a quarter of one limb
+        const uint32_t k0 = g16 * 16;
+        const uint64_t ml = gen_bits_limb(seed, kGenMaskTag, R, k0 / 64);
+        const uint64_t pl = gen_bits_limb(seed, kGenPatternTag, R, k0 / 64);
+        const uint32_t mb = (uint32_t)(ml >> (k0 % 64)) & 0xFFFFu;
+        const uint32_t pb = (uint32_t)(pl >> (k0 % 64)) & 0xFFFFu & mb;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t m0 = (mb >> (2 * e)) & 1u, m1 = (mb >> (2 * e + 1)) & 1u;
+            const uint32_t p0 = (pb >> (2 * e)) & 1u, p1 = (pb >> (2 * e + 1)) & 1u;
+            w[e] = ((m0 - 2 * p0) & 0xFFFFu) | ((m1 - 2 * p1) << 16);
+        }
+        for (uint32_t q = 0; q + 1 < n_parties; ++q) {
+            const uint64_t ps = gen_party_seed(seed, q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint64_t h = gen_share_group(ps, R, (uint64_t)g16 * 4 + t);
+                w[2 * t] = __vsub2(w[2 * t], (uint32_t)h);                 // per-halfword wrapping subtraction
+                w[2 * t + 1] = __vsub2(w[2 * t + 1], (uint32_t)(h >> 32));
+            }
+        }
+    }
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        lo[t] = __byte_perm(w[2 * t], w[2 * t + 1], 0x6420);
+        hi[t] = __byte_perm(w[2 * t], w[2 * t + 1], 0x7531);
+    }
+    const size_t off = share_offset(row0 + i, g16 * 16, 0);
+    *reinterpret_cast<uint4*>(shares + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(shares + off + kPlaneTileBytes) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+
+cudaError_t launch_generate_party_shares(uint8_t* d_shares, uint64_t seed, uint32_t party, uint32_t n_parties,
+                                         uint64_t row_id0, uint64_t row0, uint64_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    generate_party_shares_kernel<<<blocks_for(n * (IRIS_BITS / 16), 256), 256, 0, stream>>>(d_shares, seed, party, n_parties,
+                                                                                           row_id0, row0, n);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_generate(uint8_t* d_shares, uint8_t* d_masks, uint64_t seed, uint64_t row_id0, uint64_t row0,

@@ -79,6 +79,19 @@ cudaError_t launch_untile_masks(const uint8_t* d_masks, uint64_t row0, uint64_t 
 cudaError_t launch_generate(uint8_t* d_shares, uint8_t* d_masks, uint64_t seed, uint64_t row_id0, uint64_t row0,
                             uint64_t n, cudaStream_t stream);
 
+// The same database as iris_db_generate's masks, but with shares that MEAN something: row id R is the synthetic
+// Template (pattern_R, mask_R); its encoding (src/lib.rs:16-26) is split into n_parties additive shares as
+// EncodedBits::share does (src/encoded_bits.rs:23-38: n-1 uniform vectors, the last = encoding - their sum).  This
+// writes party `party`'s share rows; with n_parties = 1 the "share" is the plaintext encoding itself.
+cudaError_t launch_generate_party_shares(uint8_t* d_shares, uint64_t seed, uint32_t party, uint32_t n_parties,
+                                         uint64_t row_id0, uint64_t row0, uint64_t n, cudaStream_t stream);
+
+// Arch-level batched dots (iris_dotbatch.cu): operand images of up to 31 arbitrary vectors in the slots of the 31
+// rotations, and the gather of [groups][n][31] results into [n][n_vec].
+cudaError_t launch_prep_distance_vectors(const uint16_t* d_a, uint32_t n_vec, uint8_t* d_qd, int* d_flag, cudaStream_t stream);
+cudaError_t launch_prep_mask_vectors(const uint8_t* d_a, uint32_t n_vec, uint8_t* d_qm, uint8_t* d_qm4, cudaStream_t stream);
+cudaError_t launch_compact_columns(const uint16_t* d_in, uint64_t n, uint32_t n_vec, uint16_t* d_out, cudaStream_t stream);
+
 // CUDA-core cross-check kernels over the same tiled image (not the product path; used to verify
 // the tensor path at full size on the GPU and to serve the per-pair arch entry points).
 cudaError_t launch_simt_distances(const uint8_t* d_shares, const uint16_t* d_query, uint64_t row_begin,
@@ -122,10 +135,18 @@ struct CombineParams {
     const uint16_t* denominators;          // [n][31] u16 (device)
     uint64_t n;
     uint64_t index_base;                   // added to the row number in the reported argmin
-    double* distances_out;                 // optional [n] f64 (device)
+    double* distances_out;                 // optional [n] f64 (device); [Q][n] for a batch
+    size_t query_stride;                   // batch: elements between the [n][31] arrays of consecutive queries
 };
-size_t combine_scratch_bytes(uint64_t n);
-cudaError_t launch_combine_min(const CombineParams& p, void* scratch, void* result, cudaStream_t stream);
+struct ResultPair {                        // what a search returns per query: 16 bytes
+    double min_distance;
+    unsigned long long min_index;          // ~0 = nothing below +inf
+};
+size_t combine_scratch_bytes(uint64_t n);  // per query
+cudaError_t launch_combine_min(const CombineParams& p, void* scratch, void* result, cudaStream_t stream, uint32_t num_queries = 1);
+// out[q] = best over s < n_sets of in[s * stride + q] (lowest index on ties; ~0 indices ignored)
+cudaError_t launch_merge_pairs(const ResultPair* in, uint32_t n_sets, uint32_t stride, uint32_t n_queries, ResultPair* out,
+                               cudaStream_t stream);
 
 // Number of kernels launched by this library since load (bench.py's gpu_launches).
 uint64_t launch_count();

@@ -74,4 +74,20 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {   // splitmix64 finalise
     return z ^ (z >> 31);
 }
 
+// ---- synthetic data spec (the device generators in iris_kernels.cu follow it; the test checker restates it) ----
+constexpr uint64_t kGenMul = 0xD1342543DE82EF95ull;
+constexpr uint64_t kGenMaskTag = 0xA5A5A5A55A5A5A5Aull;      // mask limb l of row R: mix64((seed ^ tag) ^ ((R*200+l) * kGenMul))
+constexpr uint64_t kGenPatternTag = 0x5A5A5A5AA5A5A5A5ull;   // pattern limb, same form
+// four u16 share elements 4g..4g+3 of row R: the 16-bit fields of mix64(seed ^ ((R*3200+g) * kGenMul))
+__host__ __device__ inline uint64_t gen_share_group(uint64_t seed, uint64_t R, uint64_t g) {
+    return mix64(seed ^ ((R * (IRIS_BITS / 4) + g) * kGenMul));
+}
+__host__ __device__ inline uint64_t gen_bits_limb(uint64_t seed, uint64_t tag, uint64_t R, uint64_t l) {
+    return mix64((seed ^ tag) ^ ((R * IRIS_LIMBS + l) * kGenMul));
+}
+// seed of the uniform share vectors of party p (p < n_parties - 1)
+__host__ __device__ inline uint64_t gen_party_seed(uint64_t seed, uint32_t p) {
+    return mix64(seed ^ (0xC2B2AE3D27D4EB4Full * (uint64_t)(p + 1)));
+}
+
 }  // namespace iris

@@ -14,8 +14,11 @@
 // the B200 box, 1 M rows per request (tests/diagnostics/participant_bench.py): 7.4 ms = 1.35e8 rows/s at the
 // reference's 20 000-row batch (22 ms before the two stages overlapped; the scan alone is 3.9 ms).
 //
-//   iris_participant --input mpc.share-0 [--bind 127.0.0.1:1234] [--device 0] [--batch-size 20000]
-//                    [--max-requests N] [--synthetic ROWS --seed S]
+// With --devices the share file is row-sharded over several GPUs (iris_cluster_*): every GPU scans its block at the same
+// time and stores its slice of the reply into one page-locked array, which is then streamed in row order.
+//
+//   iris_participant --input mpc.share-0 [--bind 127.0.0.1:1234] [--device 0 | --devices 0,1,2,3 | --devices 0-7]
+//                    [--batch-size 20000] [--max-requests N] [--synthetic ROWS --seed S]
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
@@ -74,7 +77,7 @@ static bool write_all(int fd, const void* buf, size_t n) {
 
 int main(int argc, char** argv) {
     std::string input, bind_addr = "127.0.0.1:1234";   // reference default, src/main.rs:124
-    int device = 0;
+    std::vector<int> devices{0};
     uint64_t batch = 20000, synthetic = 0, seed = 0x1715C0DE;   // the reference's chunk, src/main.rs:428
     long max_requests = -1;
     for (int i = 1; i < argc; ++i) {
@@ -88,7 +91,29 @@ int main(int argc, char** argv) {
         };
         if (a == "--input") input = next();
         else if (a == "--bind") bind_addr = next();
-        else if (a == "--device") device = atoi(next());
+        else if (a == "--device") devices = {atoi(next())};
+        else if (a == "--devices") {                      // "0,1,2" or "0-7"
+            devices.clear();
+            std::string v = next();
+            size_t pos = 0;
+            while (pos <= v.size()) {
+                size_t comma = v.find(',', pos);
+                if (comma == std::string::npos) comma = v.size();
+                const std::string item = v.substr(pos, comma - pos);
+                const size_t dash = item.find('-');
+                if (item.empty()) {
+                } else if (dash == std::string::npos) {
+                    devices.push_back(atoi(item.c_str()));
+                } else {
+                    for (int d = atoi(item.substr(0, dash).c_str()); d <= atoi(item.substr(dash + 1).c_str()); ++d) devices.push_back(d);
+                }
+                pos = comma + 1;
+            }
+            if (devices.empty()) {
+                fprintf(stderr, "bad --devices %s\n", v.c_str());
+                return 2;
+            }
+        }
         else if (a == "--batch-size") batch = strtoull(next(), nullptr, 10);
         else if (a == "--max-requests") max_requests = atol(next());
         else if (a == "--synthetic") synthetic = strtoull(next(), nullptr, 10);
@@ -119,14 +144,19 @@ int main(int argc, char** argv) {
         }
         rows = (uint64_t)st.st_size / (IRIS_BITS * 2);
     }
-    iris_db* db = nullptr;
-    if (iris_db_create(device, rows ? rows : 1, IRIS_DB_SHARES, &db)) die("iris_db_create");
+    // one handle for the whole file: contiguous row blocks in the HBM of each GPU, loaded by all GPUs at the same time
+    iris_cluster* cluster = nullptr;
+    if (iris_cluster_create(devices.data(), (uint32_t)devices.size(), rows ? rows : 1, IRIS_DB_SHARES, &cluster)) die("iris_db_create");
     if (synthetic) {
-        if (iris_db_generate(db, seed, 0, rows)) die("iris_db_generate");
+        if (iris_cluster_generate(cluster, seed, 0, 0, 0, rows)) die("iris_cluster_generate");
     } else if (rows) {
-        if (iris_db_load_shares_file(db, input.c_str(), 0, 0)) die("iris_db_load_shares_file");
+        if (iris_cluster_load_files(cluster, input.c_str(), nullptr)) die("iris_cluster_load_files");
     }
-    fprintf(stderr, "Opened share with %llu encrypted patterns (resident in HBM on device %d)\n", (unsigned long long)rows, device);
+    const int device = devices[0];
+    iris_db* db = nullptr;                                   // the single shard of a one-GPU participant
+    if (iris_cluster_shard(cluster, 0, &db, nullptr, nullptr, nullptr)) die("iris_cluster_shard");
+    fprintf(stderr, "Opened share with %llu encrypted patterns (resident in HBM on %zu GPU%s)\n", (unsigned long long)rows,
+            devices.size(), devices.size() == 1 ? "" : "s");
 
     const size_t colon = bind_addr.rfind(':');
     if (colon == std::string::npos) {
@@ -156,6 +186,9 @@ int main(int argc, char** argv) {
     uint16_t* ring[kRing];
     for (uint16_t*& slot : ring)
         if (iris_host_alloc(batch * IRIS_ROTATIONS * sizeof(uint16_t), reinterpret_cast<void**>(&slot))) die("iris_host_alloc");
+    uint16_t* whole = nullptr;                               // several GPUs: the complete reply, written by all of them
+    if (devices.size() > 1 && iris_host_alloc((rows ? rows : 1) * IRIS_ROTATIONS * sizeof(uint16_t), reinterpret_cast<void**>(&whole)))
+        die("iris_host_alloc");
     const uint64_t n_batches = (rows + batch - 1) / batch;
     uint64_t tmpl[2 * IRIS_LIMBS];
     for (long served = 0; max_requests < 0 || served < max_requests; ++served) {
@@ -173,6 +206,14 @@ int main(int argc, char** argv) {
             continue;
         }
         fprintf(stderr, "Request received.\n");
+        if (whole) {
+            // every GPU: encode(&template), DistanceEngine::new, batch_process over its block (src/main.rs:427-430)
+            if (iris_cluster_match_template(cluster, tmpl, tmpl + IRIS_LIMBS, whole, nullptr)) die("iris_cluster_match_template");
+            const bool sent = write_all(fd, whole, rows * IRIS_ROTATIONS * sizeof(uint16_t));
+            close(fd);
+            fprintf(stderr, sent ? "Reply sent.\n" : "Peer went away.\n");
+            continue;
+        }
         iris_distance_engine* engine = nullptr;
         if (iris_distance_engine_new_from_template(device, tmpl, tmpl + IRIS_LIMBS, &engine)) die("engine");
         std::mutex mu;
@@ -234,7 +275,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, ok ? "Reply sent.\n" : "Peer went away.\n");
     }
     for (uint16_t* slot : ring) iris_host_free(slot);
+    iris_host_free(whole);
     close(ls);
-    iris_db_destroy(db);
+    iris_cluster_destroy(cluster);
     return 0;
 }

@@ -232,6 +232,21 @@ def gen_mask_rows(seed: int, row0: int, n: int, threads: int = 1) -> np.ndarray:
     return out
 
 
+def gen_pattern_rows(seed: int, row0: int, n: int, threads: int = 1) -> np.ndarray:
+    """pattern_R of the synthetic Templates (mask_R = gen_mask_rows)."""
+    out = np.empty((n, LIMBS), np.uint64)
+    load().oracle_gen_pattern_rows(ctypes.c_uint64(seed), ctypes.c_uint64(row0), ctypes.c_size_t(n), _u64p(out), ctypes.c_int(threads))
+    return out
+
+
+def gen_party_share_rows(seed: int, party: int, n_parties: int, row0: int, n: int, threads: int = 1) -> np.ndarray:
+    """Party `party`'s additive share (EncodedBits::share, src/encoded_bits.rs:23-38) of encode(Template R)."""
+    out = np.empty((n, BITS), np.uint16)
+    load().oracle_gen_party_share_rows(ctypes.c_uint64(seed), ctypes.c_uint32(party), ctypes.c_uint32(n_parties),
+                                       ctypes.c_uint64(row0), ctypes.c_size_t(n), _u16p(out), ctypes.c_int(threads))
+    return out
+
+
 # ----------------------------------------------------------------------------- numpy second opinion
 def np_bits_to_bool(bits) -> np.ndarray:
     """[..., 200] u64 -> [..., 12800] {0,1}; bit k = byte k/8, bit k%8 (src/bits.rs:44-57, test_index)."""

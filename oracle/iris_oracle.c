@@ -277,6 +277,48 @@ void oracle_gen_mask_row(uint64_t seed, uint64_t row, uint64_t *out /* [200] */)
         out[l] = mix64((seed ^ 0xA5A5A5A55A5A5A5Aull) ^ ((row * IRIS_LIMBS + l) * 0xD1342543DE82EF95ull));
 }
 
+/* Synthetic Templates and their additive shares (the data spec in csrc/iris_layout.h, restated): row R is the Template
+ * (pattern_R, mask_R) with mask_R = oracle_gen_mask_row and pattern_R drawn the same way under another tag; party p <
+ * n-1 holds a uniform vector (oracle_gen_share_row under the party's seed), the last party holds
+ * encode(Template R) - sum of the others -- EncodedBits::share, src/encoded_bits.rs:23-38, via oracle_share_last. */
+void oracle_gen_pattern_row(uint64_t seed, uint64_t row, uint64_t *out /* [200] */) {
+    for (uint64_t l = 0; l < IRIS_LIMBS; ++l)
+        out[l] = mix64((seed ^ 0x5A5A5A5AA5A5A5A5ull) ^ ((row * IRIS_LIMBS + l) * 0xD1342543DE82EF95ull));
+}
+
+static uint64_t party_seed(uint64_t seed, uint32_t p) { return mix64(seed ^ (0xC2B2AE3D27D4EB4Full * (uint64_t)(p + 1))); }
+
+void oracle_gen_party_share_row(uint64_t seed, uint32_t party, uint32_t n_parties, uint64_t row, uint16_t *out /* [12800] */) {
+    if (party + 1 < n_parties) {
+        oracle_gen_share_row(party_seed(seed, party), row, out);
+        return;
+    }
+    static _Thread_local uint16_t enc[IRIS_BITS], rest[IRIS_BITS], acc[IRIS_BITS];
+    uint64_t pattern[IRIS_LIMBS], mask[IRIS_LIMBS];
+    oracle_gen_pattern_row(seed, row, pattern);
+    oracle_gen_mask_row(seed, row, mask);
+    oracle_encode(pattern, mask, enc);
+    memset(acc, 0, sizeof acc);
+    for (uint32_t q = 0; q + 1 < n_parties; ++q) {
+        oracle_gen_share_row(party_seed(seed, q), row, rest);
+        for (int i = 0; i < IRIS_BITS; ++i) acc[i] = (uint16_t)(acc[i] + rest[i]);
+    }
+    oracle_share_last(enc, acc, 1, out);
+}
+
+void oracle_gen_party_share_rows(uint64_t seed, uint32_t party, uint32_t n_parties, uint64_t row0, size_t n, uint16_t *out, int threads) {
+    (void)threads;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+    for (long i = 0; i < (long)n; ++i)
+        oracle_gen_party_share_row(seed, party, n_parties, row0 + (uint64_t)i, out + (size_t)i * IRIS_BITS);
+}
+
+void oracle_gen_pattern_rows(uint64_t seed, uint64_t row0, size_t n, uint64_t *out, int threads) {
+    (void)threads;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+    for (long i = 0; i < (long)n; ++i) oracle_gen_pattern_row(seed, row0 + (uint64_t)i, out + (size_t)i * IRIS_LIMBS);
+}
+
 void oracle_gen_share_rows(uint64_t seed, uint64_t row0, size_t n, uint16_t *out, int threads) {
     (void)threads;
 #pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
