@@ -26,6 +26,10 @@ pub struct IrisDistanceEngine {
 pub struct IrisMasksEngine {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct IrisCluster {
+    _private: [u8; 0],
+}
 
 pub const IRIS_DB_SHARES: u32 = 1;
 pub const IRIS_DB_MASKS: u32 = 2;
@@ -92,6 +96,42 @@ extern "C" {
         min_distance: *mut f64,
         min_index: *mut u64,
     ) -> c_int;
+    // Arch-level grids: every pair of `a` and `b` vectors in one call (the criterion grid of arch/mod.rs:22-72).
+    fn iris_dot_u16_batch(device: c_int, a: *const u16, n_a: u32, b: *const u16, n_b: u64, out: *mut u16) -> c_int;
+    fn iris_dot_bool_batch(device: c_int, a: *const u64, n_a: u32, b: *const u64, n_b: u64, out: *mut u16) -> c_int;
+    // One database row-sharded over the GPUs of the box.
+    fn iris_cluster_create(
+        devices: *const c_int,
+        n_devices: u32,
+        capacity_rows: u64,
+        flags: u32,
+        out: *mut *mut IrisCluster,
+    ) -> c_int;
+    fn iris_cluster_destroy(c: *mut IrisCluster) -> c_int;
+    fn iris_cluster_len(c: *const IrisCluster, n_shards: *mut u32, n_shares: *mut u64, n_masks: *mut u64) -> c_int;
+    fn iris_cluster_load_files(c: *mut IrisCluster, shares_path: *const c_char, masks_path: *const c_char) -> c_int;
+    fn iris_cluster_load_rows(c: *mut IrisCluster, shares: *const u16, masks: *const u64, n: u64) -> c_int;
+    fn iris_cluster_match(
+        c: *mut IrisCluster,
+        query: *const u16,
+        query_mask: *const u64,
+        distances_out: *mut u16,
+        denominators_out: *mut u16,
+    ) -> c_int;
+    fn iris_cluster_match_template(
+        c: *mut IrisCluster,
+        pattern: *const u64,
+        mask: *const u64,
+        distances_out: *mut u16,
+        denominators_out: *mut u16,
+    ) -> c_int;
+    fn iris_cluster_search(
+        c: *mut IrisCluster,
+        templates: *const u64,
+        num_queries: u32,
+        min_distance: *mut f64,
+        min_index: *mut u64,
+    ) -> c_int;
     // Page-locked result buffers (instead of a fresh Vec per chunk, main.rs:429, 514) and device buffers.
     #[allow(dead_code)]
     fn iris_host_alloc(bytes: u64, out: *mut *mut c_void) -> c_int;
@@ -123,6 +163,88 @@ pub fn dot_bool(a: &[u64; LIMBS], b: &[u64; LIMBS]) -> u16 {
     let mut out = 0u16;
     check(unsafe { iris_dot_bool(0, a.as_ptr(), b.as_ptr(), &mut out) });
     out
+}
+
+/// The criterion grid of arch/mod.rs:46-72 in one call: `out[i][j] = dot_u16(a[j], b[i])`.
+pub fn dot_u16_grid(a: &[[u16; BITS]], b: &[[u16; BITS]]) -> Vec<u16> {
+    let mut out = vec![0u16; a.len() * b.len()];
+    check(unsafe {
+        iris_dot_u16_batch(0, a.as_ptr().cast(), a.len() as u32, b.as_ptr().cast(), b.len() as u64, out.as_mut_ptr())
+    });
+    out
+}
+
+/// The criterion grid of arch/mod.rs:22-44 for `dot_bool`.
+pub fn dot_bool_grid(a: &[[u64; LIMBS]], b: &[[u64; LIMBS]]) -> Vec<u16> {
+    let mut out = vec![0u16; a.len() * b.len()];
+    check(unsafe {
+        iris_dot_bool_batch(0, a.as_ptr().cast(), a.len() as u32, b.as_ptr().cast(), b.len() as u64, out.as_mut_ptr())
+    });
+    out
+}
+
+/// One database row-sharded over several GPUs (main.rs:386-400 mmaps the whole file; here every GPU holds a
+/// contiguous block of rows in HBM and the library runs one host thread + stream per GPU).
+pub struct Cluster(*mut IrisCluster);
+unsafe impl Send for Cluster {}
+
+impl Cluster {
+    pub fn new(devices: &[i32], capacity_rows: u64, flags: u32) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { iris_cluster_create(devices.as_ptr(), devices.len() as u32, capacity_rows, flags, &mut h) });
+        Self(h)
+    }
+
+    /// `mpc.share-i` / `mpc.masks` as written by `prepare` (main.rs:337-371); every GPU reads its own block.
+    pub fn load_files(&self, shares: Option<&CStr>, masks: Option<&CStr>) {
+        check(unsafe {
+            iris_cluster_load_files(
+                self.0,
+                shares.map_or(ptr::null(), |p| p.as_ptr()),
+                masks.map_or(ptr::null(), |p| p.as_ptr()),
+            )
+        });
+    }
+
+    pub fn len(&self) -> usize {
+        let (mut s, mut m, mut n) = (0u64, 0u64, 0u32);
+        check(unsafe { iris_cluster_len(self.0, &mut n, &mut s, &mut m) });
+        s.max(m) as usize
+    }
+
+    /// The participant's request (main.rs:419-431): distances of the whole database for one template.
+    pub fn distances(&self, template: &Template, out: &mut [[u16; 31]]) {
+        check(unsafe {
+            iris_cluster_match_template(
+                self.0,
+                template.pattern.0.as_ptr(),
+                template.mask.0.as_ptr(),
+                out.as_mut_ptr().cast(),
+                ptr::null_mut(),
+            )
+        });
+    }
+
+    /// The coordinator's side (main.rs:510-516): denominators of the whole database for one query mask.
+    pub fn denominators(&self, mask: &Bits, out: &mut [[u16; 31]]) {
+        check(unsafe { iris_cluster_match(self.0, ptr::null(), mask.0.as_ptr(), ptr::null_mut(), out.as_mut_ptr().cast()) });
+    }
+
+    /// Whole search on the GPUs for a cluster holding plain encodings: (min distance, row) per template.
+    pub fn search(&self, templates: &[Template]) -> Vec<(f64, usize)> {
+        let mut d = vec![f64::INFINITY; templates.len()];
+        let mut i = vec![u64::MAX; templates.len()];
+        check(unsafe {
+            iris_cluster_search(self.0, templates.as_ptr().cast(), templates.len() as u32, d.as_mut_ptr(), i.as_mut_ptr())
+        });
+        d.into_iter().zip(i.into_iter().map(|x| x as usize)).collect()
+    }
+}
+
+impl Drop for Cluster {
+    fn drop(&mut self) {
+        unsafe { iris_cluster_destroy(self.0) };
+    }
 }
 
 /// HBM-resident database: replaces the `Arc<Mmap>` + `cast_slice` of main.rs:389-391 / 458-461.

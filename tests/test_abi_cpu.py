@@ -130,3 +130,55 @@ def test_wrapper_validates_buffers():
         api._ptr(np.zeros(10, np.uint16), np.uint16, iris.BITS, "q")
     with pytest.raises(ValueError):
         api._ptr(np.zeros((4, iris.BITS), np.uint16)[:, ::2], np.uint16, 1, "q")
+
+
+# ---------------------------------------------------------------------------------- Rust binding stays in sync
+_C2RUST = {
+    "int": "c_int", "uint64_t": "u64", "uint32_t": "u32", "const char*": "*const c_char", "void*": "*mut c_void",
+    "void**": "*mut *mut c_void", "const void*": "*const c_void", "const uint16_t*": "*const u16", "uint16_t*": "*mut u16",
+    "const uint64_t*": "*const u64", "uint64_t*": "*mut u64", "uint32_t*": "*mut u32", "double*": "*mut f64",
+    "const int*": "*const c_int", "int*": "*mut c_int", "const uint16_t*const*": "*const *const u16",
+    "iris_db*": "*mut IrisDb", "iris_db**": "*mut *mut IrisDb", "const iris_db*": "*const IrisDb",
+    "iris_distance_engine*": "*mut IrisDistanceEngine", "iris_distance_engine**": "*mut *mut IrisDistanceEngine",
+    "iris_masks_engine*": "*mut IrisMasksEngine", "iris_masks_engine**": "*mut *mut IrisMasksEngine",
+    "iris_cluster*": "*mut IrisCluster", "iris_cluster**": "*mut *mut IrisCluster", "const iris_cluster*": "*const IrisCluster",
+}
+
+
+def _c_prototypes():
+    text = open(os.path.join(ROOT, "include", "iris_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|uint64_t|const char \*)\s*\**(iris_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = []
+        for a in [x.strip() for x in args.split(",") if x.strip() and x.strip() != "void"]:
+            a = re.sub(r"\[[^\]]*\]", "*", a)                      # array parameters decay to pointers
+            m = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)?\s*(\**)$", a)
+            m = re.match(r"^(.*?[\s\*])([A-Za-z_][A-Za-z0-9_]*)(\**)$", a)
+            ctype = (m.group(1) + m.group(3)) if m else a
+            params.append(re.sub(r"\s+", " ", ctype).replace(" *", "*").replace("* ", "*").strip())
+        protos[name] = params
+    return protos
+
+
+def _rust_prototypes():
+    text = open(os.path.join(ROOT, "integration", "rust", "src", "arch", "cuda.rs")).read()
+    block = text[text.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    block = re.sub(r"//[^\n]*", "", block)
+    protos = {}
+    for name, args in re.findall(r"fn\s+(iris_[a-z0-9_]+)\s*\(([^)]*)\)", block, flags=re.S):
+        params = [re.sub(r"\s+", " ", a.split(":", 1)[1]).strip() for a in args.split(",") if ":" in a]
+        protos[name] = params
+    return protos
+
+
+def test_rust_extern_block_matches_the_header():
+    """integration/rust/src/arch/cuda.rs cannot be compiled here (no Rust toolchain): keep at least its extern "C"
+    declarations identical, name by name and parameter by parameter, to include/iris_b200.h."""
+    c, r = _c_prototypes(), _rust_prototypes()
+    assert len(r) >= 30
+    for name, rparams in r.items():
+        assert name in c, f"{name} is bound in cuda.rs but not declared in iris_b200.h"
+        want = [_C2RUST[p] for p in c[name]]
+        assert rparams == want, f"{name}: cuda.rs has {rparams}, the header means {want}"

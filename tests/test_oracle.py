@@ -234,3 +234,35 @@ def test_golden_fixture():
     secret = (((i // O.COLS) << 8) | (i % O.COLS)).astype(np.uint16)
     for a_str, head in kn.items():
         assert O.encoded_rotated(secret, int(a_str))[: len(head)].tolist() == head
+
+
+def test_synthetic_party_shares_are_a_secret_sharing_of_the_encodings():
+    """The synthetic database spec (restated in oracle/iris_oracle.c): row R is encode(pattern_R, mask_R) split like
+    EncodedBits::share (src/encoded_bits.rs:23-38).  Shares sum to the encoding, single shares look uniform, and the
+    coordinator's combine over the three parties' distances (src/main.rs:597-621) equals Template::distance in the
+    clear (src/template.rs:43-64) -- on every row, so a planted near-duplicate is what a search returns."""
+    seed, n, parties = 0x1715C0DE, 40, 3
+    pats, masks = O.gen_pattern_rows(seed, 100, n), O.gen_mask_rows(seed, 100, n)
+    enc = np.stack([O.encode(pats[i], masks[i]) for i in range(n)])
+    shares = [O.gen_party_share_rows(seed, p, parties, 100, n, threads=2) for p in range(parties)]
+    total = np.zeros_like(enc)
+    for s in shares:
+        total = (total + s).astype(np.uint16)
+    assert np.array_equal(total, enc)
+    assert np.array_equal(O.gen_party_share_rows(seed, 0, 1, 100, n), enc)
+    for s in shares:
+        assert 32000 < s.mean() < 33500 and len(np.unique(s[0])) > 5000
+    # query: row 117 with 1 000 pattern bits flipped, rotated by +3 columns
+    rng = np.random.default_rng(1)
+    bits = O.np_bits_to_bool(pats[17]).copy()
+    bits[rng.choice(O.BITS, size=1000, replace=False)] ^= 1
+    qp, qm = O.bits_rotated(O.np_bool_to_bits(bits), 3), O.bits_rotated(masks[17], 3)
+    q = O.encode(qp, qm)
+    dist = np.stack([O.distance_batch(q, s) for s in shares])
+    md, mi = O.combine_min(dist, O.masks_batch(qm, masks))
+    plain = [O.template_distance(qp, qm, pats[i], masks[i]) for i in range(n)]
+    assert mi == 17 == int(np.argmin(plain)) and md == plain[17] and md < 0.2
+    for i in (0, 5, 39):
+        one = O.decode_distance(((dist[0][i].astype(np.uint32) + dist[1][i] + dist[2][i]) & 0xFFFF).astype(np.uint16),
+                                O.masks_batch(qm, masks[i:i + 1])[0])
+        assert one == plain[i]
