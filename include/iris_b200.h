@@ -166,6 +166,20 @@ int iris_masks_engine_batch_process_resident(iris_masks_engine *e, uint16_t *out
 int iris_match_resident(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
                         uint64_t row_end, uint16_t *distances_out, uint16_t *denominators_out);
 
+/* The same fused scan with HOST result arrays, reporting progress: `progress(user, b, e)` is called on the calling thread
+ * each time the rows [b, e) (database rows, in ascending order, together covering [row_begin,row_end)) are complete in
+ * host memory, while the scan of the following rows is already running -- so a caller can stream the reply out (the
+ * participant's socket loop, src/main.rs:437-443) while the GPU is still scanning. */
+typedef void (*iris_progress_fn)(void *user, uint64_t row_begin, uint64_t row_end);
+int iris_match_resident_streamed(iris_distance_engine *de, iris_masks_engine *me, iris_db *db, uint64_t row_begin,
+                                 uint64_t row_end, uint16_t *distances_out, uint16_t *denominators_out,
+                                 iris_progress_fn progress, void *user);
+/* Consecutive scans of one shard with device outputs that do not overlap in memory may overlap in time: the next scan
+ * starts on the SMs the previous scan's last partial wave leaves idle (the reference calls batch_process on 20 000-row
+ * chunks, src/main.rs:427-430: 157 tiles on 148 SMs).  On by default, on the library's stream and on a caller's stream
+ * alike; a scan never starts early behind a kernel that is not a scan of this shard.  allow = 0 turns it off. */
+int iris_db_set_overlap(iris_db *db, int allow);
+
 /* ---- batched queries (BASELINE config 4): num_queries DistanceEngines against the same rows as ONE dense
  * int8 GEMM on the tensor cores; num_queries MasksEngines four at a time over the 4-bit operand expanded into
  * tensor memory.  Equivalent to calling batch_process_resident once per engine;
@@ -250,6 +264,11 @@ int iris_cluster_match(iris_cluster *c, const uint16_t *query, const uint64_t *q
 /* The participant's request (src/main.rs:419-431): encode(&template) on each GPU, distances of the whole cluster. */
 int iris_cluster_match_template(iris_cluster *c, const uint64_t *pattern, const uint64_t *mask, uint16_t *distances_out,
                                 uint16_t *denominators_out);
+/* The same with HOST outputs and progress reports (see iris_match_resident_streamed): `progress` is called with ranges of
+ * CLUSTER rows, from the library's per-GPU threads (several at a time, each GPU's ranges in ascending order). */
+int iris_cluster_match_template_streamed(iris_cluster *c, const uint64_t *pattern, const uint64_t *mask,
+                                         uint16_t *distances_out, uint16_t *denominators_out, iris_progress_fn progress,
+                                         void *user);
 /* Search: num_queries wire Templates ([num_queries][400] u64 = {pattern[200], mask[200]}) against a cluster that
  * holds whole encodings (n_parties = 1): per query the minimum decoded distance over all rows and rotations and the
  * row attaining it (lowest row on ties; UINT64_MAX when nothing is below +inf) -- the coordinator's loop

@@ -38,4 +38,5 @@ from .api import (  # noqa: F401
     lib,
     library_path,
     match,
+    match_streamed,
 )

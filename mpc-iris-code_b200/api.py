@@ -24,6 +24,7 @@ IRIS_DB_MASKS = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64)   # iris_progress_fn
 
 
 class IrisError(RuntimeError):
@@ -88,6 +89,9 @@ def lib():
         "iris_cluster_match": [vp, vp, vp, vp, vp],
         "iris_cluster_match_template": [vp, vp, vp, vp, vp],
         "iris_cluster_search": [vp, vp, u32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
+        "iris_cluster_match_template_streamed": [vp, vp, vp, vp, vp, PROGRESS_FN, vp],
+        "iris_match_resident_streamed": [vp, vp, vp, u64, u64, vp, vp, PROGRESS_FN, vp],
+        "iris_db_set_overlap": [vp, i32],
         "iris_comm_unique_id": [vp],
         "iris_cluster_join": [vp, vp, i32, i32],
         "iris_db_load_shares_file": [vp, ctypes.c_char_p, u64, u64],
@@ -320,6 +324,10 @@ class Database:
         _check(lib().iris_db_read_masks(self._h, row_begin, n, out.ctypes.data))
         return out
 
+    def set_overlap(self, allow: bool) -> None:
+        """Whether consecutive device-output scans of this shard may overlap each other's tails (default: yes)."""
+        _check(lib().iris_db_set_overlap(self._h, 1 if allow else 0))
+
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         _check(lib().iris_db_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 
@@ -463,6 +471,18 @@ def match(distance_engine: Optional[DistanceEngine], masks_engine: Optional[Mask
         db._h, row_begin, row_end,
         _ptr(distances_out, np.uint16, n, "distances_out") if distance_engine else None,
         _ptr(denominators_out, np.uint16, n, "denominators_out") if masks_engine else None))
+
+
+def match_streamed(distance_engine, masks_engine, db: Database, row_begin: int, row_end: int, distances_out, denominators_out,
+                   progress) -> None:
+    """match() with HOST outputs; progress(b, e) is called as the rows [b, e) land in host memory while later rows
+    are still being scanned (iris_match_resident_streamed)."""
+    n = (row_end - row_begin) * ROTATIONS
+    cb = PROGRESS_FN(lambda _u, b, e: progress(b, e))
+    _check(lib().iris_match_resident_streamed(
+        distance_engine._h if distance_engine else None, masks_engine._h if masks_engine else None, db._h, row_begin, row_end,
+        _ptr(distances_out, np.uint16, n, "distances_out") if distance_engine else None,
+        _ptr(denominators_out, np.uint16, n, "denominators_out") if masks_engine else None, cb, None))
 
 
 def distances_batch(engines, db: Database, row_begin: int, row_end: int, out) -> None:
@@ -624,6 +644,15 @@ class Cluster:
         _check(lib().iris_cluster_match_template(self._h, _ptr(pattern, np.uint64, LIMBS, "pattern"), _ptr(mask, np.uint64, LIMBS, "mask"),
                                                  _ptr(distances_out, np.uint16, n, "distances_out"),
                                                  _ptr(denominators_out, np.uint16, n, "denominators_out")))
+
+    def match_template_streamed(self, pattern, mask, distances_out, progress, denominators_out=None) -> None:
+        """match_template with HOST outputs; progress(b, e) is called (from the library's per-GPU threads) as cluster
+        rows [b, e) land in host memory."""
+        n = len(self) * ROTATIONS
+        cb = PROGRESS_FN(lambda _u, b, e: progress(b, e))
+        _check(lib().iris_cluster_match_template_streamed(
+            self._h, _ptr(pattern, np.uint64, LIMBS, "pattern"), _ptr(mask, np.uint64, LIMBS, "mask"),
+            _ptr(distances_out, np.uint16, n, "distances_out"), _ptr(denominators_out, np.uint16, n, "denominators_out"), cb, None))
 
     def search(self, templates):
         """templates: [Q][400] u64 wire Templates -> (min distances [Q] f64, rows [Q] i64, -1 = none)."""

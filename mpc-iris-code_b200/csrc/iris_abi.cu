@@ -110,6 +110,7 @@ struct iris_db {
     static constexpr int kChain = 6;
     uintptr_t chain_lo[kChain][2] = {}, chain_hi[kChain][2] = {};
     int chain_len = 0;
+    bool overlap = true;             // consecutive device-output scans of this shard may overlap (iris_db_set_overlap)
 };
 
 // Shards that are alive (engines remember the shard they last scanned so that their buffers are released in stream
@@ -406,6 +407,7 @@ extern "C" int iris_db_set_stream(iris_db* db, void* cuda_stream) {
     DeviceGuard g(db->device);
     CK(cudaStreamSynchronize(db->stream));
     db->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : db->own_stream;
+    db->chain_len = 0;               // everything launched so far has completed
     return IRIS_OK;
 }
 
@@ -660,9 +662,14 @@ static int engine_resolve(iris_distance_engine* e) {
     return IRIS_OK;
 }
 
+struct Progress {                 // host outputs only: called on the calling thread as blocks of rows become complete
+    iris_progress_fn fn = nullptr;
+    void* user = nullptr;
+};
+
 // de / me: the engines whose operand images are scanned (nullptr = that half is not computed).
 static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* me, uint64_t row_begin, uint64_t row_end,
-                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev) {
+                     uint16_t* dist_out, uint16_t* den_out, int32_t* raw_dev, const Progress* progress = nullptr) {
     if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
     if (!de && !me) return fail(IRIS_ERR_INVALID, "no engine given");
     const uint8_t* qd = de ? de->d_qd : nullptr;
@@ -716,11 +723,13 @@ static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* m
         // The reference calls batch_process chunk after chunk (src/main.rs:427-430): consecutive scans on the library's
         // own stream with disjoint outputs may overlap (the next one starts on the SMs the previous one's tail leaves
         // idle).  After kChain chained launches one ordinary launch drains the chain, so the ranges below are all a
-        // running scan can belong to.  Never on a caller-supplied stream: its other work is unknown.
+        // running scan can belong to.  The same holds on a caller-supplied stream: a scan only ever starts early behind
+        // another scan of this shard (a foreign kernel in between never triggers the programmatic launch, so the scan
+        // behind it starts when that kernel has completed); iris_db_set_overlap(db, 0) turns the overlap off.
         const size_t bytes = (size_t)(row_end - row_begin) * kOutRowBytes;
         const uintptr_t lo[2] = {reinterpret_cast<uintptr_t>(dist_out), reinterpret_cast<uintptr_t>(den_out)};
         const uintptr_t hi[2] = {dist_out ? lo[0] + bytes : 0, den_out ? lo[1] + bytes : 0};
-        bool chain = db->stream == db->own_stream && !raw_dev && db->chain_len < iris_db::kChain;
+        bool chain = db->overlap && !raw_dev && db->chain_len < iris_db::kChain;
         for (int i = 0; chain && i < db->chain_len; ++i)
             for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 2; ++b)
@@ -747,6 +756,7 @@ static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* m
     // the only one that is not hidden behind a scan, so it should be short.
     const uint64_t wave_rows = (uint64_t)db->num_sms * kTileRows;
     uint64_t next_edge = aligned0;
+    uint64_t prev_b = row_begin, prev_e = row_begin;           // the chunk enqueued one iteration ago (progress reports)
     for (uint64_t i = 0; cb < row_end; ++i) {
         const uint64_t remaining = row_end > next_edge ? row_end - next_edge : 0;
         uint64_t step = chunk_rows;
@@ -770,13 +780,27 @@ static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* m
         if (qm && !den_dev)
             CK(cudaMemcpyAsync(den_out + (cb - row_begin) * IRIS_ROTATIONS, db->d_res[b][1], bytes, cudaMemcpyDeviceToHost, db->copy_stream));
         CK(cudaEventRecord(db->ev_copy[b], db->copy_stream));
+        if (progress && progress->fn) {
+            // the device now has chunk i queued behind chunk i-1: wait for i-1 to be in host memory and report it
+            if (prev_e > prev_b) {
+                CK(cudaEventSynchronize(db->ev_copy[b ^ 1]));
+                int rce = check_error_flag(db);
+                if (rce) return rce;
+                progress->fn(progress->user, prev_b, prev_e);
+            }
+            prev_b = cb;
+            prev_e = ce;
+        }
         cb = ce;
     }
     int rc2 = sync_checked(db, db->copy_stream);
     if (rc2) return rc2;
     rc2 = sync_checked(db, db->stream);
     if (rc2) return rc2;
-    return check_error_flag(db);
+    rc2 = check_error_flag(db);
+    if (rc2) return rc2;
+    if (progress && progress->fn && prev_e > prev_b) progress->fn(progress->user, prev_b, prev_e);
+    return IRIS_OK;
 }
 
 // ------------------------------------------------------------------------------------ engines
@@ -1175,6 +1199,29 @@ extern "C" int iris_match_resident(iris_distance_engine* de, iris_masks_engine* 
     if ((de && de->device != db->device) || (me && me->device != db->device))
         return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
     return scan_core(db, de, me, row_begin, row_end, distances_out, denominators_out, nullptr);
+}
+
+extern "C" int iris_match_resident_streamed(iris_distance_engine* de, iris_masks_engine* me, iris_db* db, uint64_t row_begin,
+                                            uint64_t row_end, uint16_t* distances_out, uint16_t* denominators_out,
+                                            iris_progress_fn progress, void* user) {
+    if (!db || (!de && !me)) return fail(IRIS_ERR_INVALID, "NULL handle");
+    if ((de && de->device != db->device) || (me && me->device != db->device))
+        return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
+    if ((de && is_device_pointer(distances_out)) || (me && is_device_pointer(denominators_out)))
+        return fail(IRIS_ERR_INVALID, "the streamed form takes HOST result arrays");
+    Progress pr;
+    pr.fn = progress;
+    pr.user = user;
+    return scan_core(db, de, me, row_begin, row_end, distances_out, denominators_out, nullptr, &pr);
+}
+
+extern "C" int iris_db_set_overlap(iris_db* db, int allow) {
+    if (!db) return fail(IRIS_ERR_INVALID, "db is NULL");
+    DeviceGuard g(db->device);
+    CK(cudaStreamSynchronize(db->stream));
+    db->overlap = allow != 0;
+    db->chain_len = 0;
+    return IRIS_OK;
 }
 
 extern "C" int iris_distances(int device, const uint16_t* query, const uint16_t* entry, uint16_t* out) {

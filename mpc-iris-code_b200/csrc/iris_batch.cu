@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "iris_epilogue.cuh"
 #include "iris_kernels.cuh"
@@ -250,6 +251,13 @@ static cudaError_t launch_batch_t(const BatchParams& p, int num_sms, cudaStream_
     const uint32_t tiles = (p.pair_end - p.pair_begin) * num_groups;
     if (tiles == 0) return cudaSuccess;
     uint32_t clusters = (uint32_t)num_sms / 2;
+#ifdef IRIS_DIAGNOSTICS
+    static const int forced = [] {                      // diagnostics build only: A/B runs of the cluster count
+        const char* e = getenv("IRIS_BATCH_CLUSTERS");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0 && (uint32_t)forced < clusters) clusters = (uint32_t)forced;
+#endif
     if (tiles < clusters) clusters = tiles;
     batch_distances_kernel<SIGNED_Q><<<2 * clusters, kBatchThreads, Cfg::kSmemBytes, stream>>>(p);
     count_launch_external();

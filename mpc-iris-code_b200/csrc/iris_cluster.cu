@@ -222,6 +222,7 @@ bool peer_ok(iris_cluster* c, int from, int to) {
 // Runs fn(shard index) on every shard's thread; first failure wins (its message becomes the caller's last error).
 int run_all(iris_cluster* c, const std::function<int(uint32_t)>& fn) {
     const uint32_t n = (uint32_t)c->shards.size();
+    if (n == 1) return fn(0);                      // one shard: the calling thread submits (no hand-over latency)
     for (uint32_t i = 0; i < n; ++i) c->shards[i].worker->post([&fn, i] { return fn(i); });
     int rc = IRIS_OK;
     std::string err;
@@ -508,8 +509,18 @@ int block_finish(const Shard& s, BlockOut& b) {
     return rc;
 }
 
+struct ShardProgress {            // forwards a shard's progress reports as ranges of cluster rows
+    iris_progress_fn fn;
+    void* user;
+    uint64_t offset;
+};
+void shard_progress(void* u, uint64_t b, uint64_t e) {
+    const ShardProgress* sp = static_cast<const ShardProgress*>(u);
+    sp->fn(sp->user, sp->offset + b, sp->offset + e);
+}
+
 int cluster_match(iris_cluster* c, const uint16_t* query, const uint64_t* pattern, const uint64_t* mask, bool want_den,
-                  uint16_t* distances_out, uint16_t* denominators_out) {
+                  uint16_t* distances_out, uint16_t* denominators_out, iris_progress_fn progress = nullptr, void* user = nullptr) {
     const bool want_dist = query || pattern;
     if (!want_dist && !want_den) return cfail(IRIS_ERR_INVALID, "no query given");
     if (want_dist && !distances_out && c->n_shares) return cfail(IRIS_ERR_INVALID, "distances output is NULL");
@@ -542,7 +553,12 @@ int cluster_match(iris_cluster* c, const uint16_t* query, const uint64_t* patter
             if (want_den && (r = iris_masks_engine_new(s.device, mask, &me))) return r;
             if (de && (r = block_out(c, s, distances_out, &bd))) return r;
             if (me && (r = block_out(c, s, denominators_out, &bn))) return r;
-            r = iris_match_resident(de, me, s.db, 0, cnt, bd.direct, bn.direct);
+            if (progress) {
+                ShardProgress sp{progress, user, s.begin};
+                r = iris_match_resident_streamed(de, me, s.db, 0, cnt, bd.direct, bn.direct, shard_progress, &sp);
+            } else {
+                r = iris_match_resident(de, me, s.db, 0, cnt, bd.direct, bn.direct);
+            }
             if (r) return r;
             if ((r = block_finish(s, bd))) return r;
             if ((r = block_finish(s, bn))) return r;
@@ -572,6 +588,14 @@ extern "C" int iris_cluster_match_template(iris_cluster* c, const uint64_t* patt
     if (!c) return cfail(IRIS_ERR_INVALID, "cluster is NULL");
     if (!pattern || !mask) return cfail(IRIS_ERR_INVALID, "NULL template");
     return cluster_match(c, nullptr, pattern, mask, denominators_out != nullptr, distances_out, denominators_out);
+}
+
+extern "C" int iris_cluster_match_template_streamed(iris_cluster* c, const uint64_t* pattern, const uint64_t* mask,
+                                                    uint16_t* distances_out, uint16_t* denominators_out,
+                                                    iris_progress_fn progress, void* user) {
+    if (!c) return cfail(IRIS_ERR_INVALID, "cluster is NULL");
+    if (!pattern || !mask) return cfail(IRIS_ERR_INVALID, "NULL template");
+    return cluster_match(c, nullptr, pattern, mask, denominators_out != nullptr, distances_out, denominators_out, progress, user);
 }
 
 // ------------------------------------------------------------------------------------ search: (min, argmin) per query

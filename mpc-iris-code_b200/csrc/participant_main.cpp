@@ -9,13 +9,16 @@
 // One request at a time, like the reference.  An unmodified reference coordinator / benchmark
 // (src/main.rs:486-504, 645-686) can connect to this process.
 //
-// Same two-stage shape as the reference: a worker thread scans batch after batch into a small ring of page-locked
-// buffers (the channel) while the main thread writes finished batches to the socket.  Measured over loopback on
-// the B200 box, 1 M rows per request (tests/diagnostics/participant_bench.py): 7.4 ms = 1.35e8 rows/s at the
-// reference's 20 000-row batch (22 ms before the two stages overlapped; the scan alone is 3.9 ms).
-//
-// With --devices the share file is row-sharded over several GPUs (iris_cluster_*): every GPU scans its block at the same
-// time and stores its slice of the reply into one page-locked array, which is then streamed in row order.
+// Same two-stage shape as the reference: a worker thread produces, the connection's loop streams.
+//   one GPU      the worker scans batch after batch into a ring of three page-locked buffers (the channel) and the
+//                main thread writes finished batches to the socket.  The ring's back-pressure keeps the producer one or
+//                two batches ahead of the socket, so the bytes write() reads are still in the CPU's cache: over
+//                loopback the single TCP stream is the limit (7.4 ms per 1 M rows = 8.4 GB/s on the wire; the scan
+//                alone is 3.6 ms).  [One whole-range call into a 62 MB array frees the GPU after 3.9 ms with the first
+//                byte out after 1 ms, but write() then reads cold memory and the request takes 10 ms.]
+//   --devices    the share file is row-sharded over several GPUs (iris_cluster_*): ONE library call per request scans
+//                every block at the same time into one page-locked array and reports the rows that have landed; the
+//                main thread writes the completed prefix.  The wire is the limit by a wide margin here.
 //
 //   iris_participant --input mpc.share-0 [--bind 127.0.0.1:1234] [--device 0 | --devices 0,1,2,3 | --devices 0-7]
 //                    [--batch-size 20000] [--max-requests N] [--synthetic ROWS --seed S]
@@ -189,6 +192,33 @@ int main(int argc, char** argv) {
     uint16_t* whole = nullptr;                               // several GPUs: the complete reply, written by all of them
     if (devices.size() > 1 && iris_host_alloc((rows ? rows : 1) * IRIS_ROTATIONS * sizeof(uint16_t), reinterpret_cast<void**>(&whole)))
         die("iris_host_alloc");
+    uint32_t n_shards = 0;
+    if (iris_cluster_len(cluster, &n_shards, nullptr, nullptr)) die("iris_cluster_len");
+    std::vector<uint64_t> shard_begin(n_shards), shard_end(n_shards);
+    for (uint32_t i = 0; i < n_shards; ++i)
+        if (iris_cluster_shard(cluster, i, nullptr, nullptr, &shard_begin[i], &shard_end[i])) die("iris_cluster_shard");
+    struct Shared {
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<uint64_t> done;          // per shard: cluster rows [shard_begin, done) are in host memory
+        const std::vector<uint64_t>* begin = nullptr;
+        bool finished = false;
+        int rc = 0;
+        std::string error;
+    } sh;
+    sh.begin = &shard_begin;
+    // called by the library's per-GPU threads as blocks of rows land in `whole`
+    auto on_progress = [](void* user, uint64_t, uint64_t e) {
+        Shared* s = static_cast<Shared*>(user);
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            size_t i = s->begin->size();
+            while (i-- > 0)
+                if (e > (*s->begin)[i]) break;               // the shard whose block contains row e - 1
+            s->done[i] = e;
+        }
+        s->cv.notify_all();
+    };
     const uint64_t n_batches = (rows + batch - 1) / batch;
     uint64_t tmpl[2 * IRIS_LIMBS];
     for (long served = 0; max_requests < 0 || served < max_requests; ++served) {
@@ -207,11 +237,54 @@ int main(int argc, char** argv) {
         }
         fprintf(stderr, "Request received.\n");
         if (whole) {
-            // every GPU: encode(&template), DistanceEngine::new, batch_process over its block (src/main.rs:427-430)
-            if (iris_cluster_match_template(cluster, tmpl, tmpl + IRIS_LIMBS, whole, nullptr)) die("iris_cluster_match_template");
-            const bool sent = write_all(fd, whole, rows * IRIS_ROTATIONS * sizeof(uint16_t));
+            // several GPUs: encode(&template), DistanceEngine::new, batch_process over every block at the same time
+            // (src/main.rs:427-430) in ONE library call; the rows that have landed are streamed in row order
+            {
+                std::lock_guard<std::mutex> lk(sh.mu);
+                sh.done = shard_begin;
+                sh.finished = false;
+                sh.rc = 0;
+            }
+            std::thread producer([&] {
+                const int rc = rows ? iris_cluster_match_template_streamed(cluster, tmpl, tmpl + IRIS_LIMBS, whole, nullptr,
+                                                                           on_progress, &sh)
+                                    : 0;
+                {
+                    std::lock_guard<std::mutex> lk(sh.mu);
+                    if (rc) sh.error = iris_last_error();    // thread-local: capture it on this thread
+                    sh.rc = rc;
+                    sh.finished = true;
+                }
+                sh.cv.notify_all();
+            });
+            bool sent_all = true;
+            uint64_t sent = 0;
+            while (sent_all && sent < rows) {
+                uint64_t upto = sent;
+                {
+                    std::unique_lock<std::mutex> lk(sh.mu);
+                    auto prefix = [&] {
+                        uint64_t p = 0;
+                        for (uint32_t i = 0; i < n_shards; ++i) {
+                            p = sh.done[i];
+                            if (sh.done[i] < shard_end[i]) break;
+                        }
+                        return p;
+                    };
+                    sh.cv.wait(lk, [&] { return prefix() > sent || (sh.finished && sh.rc); });
+                    if (sh.finished && sh.rc) break;
+                    upto = prefix();
+                }
+                sent_all = write_all(fd, whole + sent * IRIS_ROTATIONS, (upto - sent) * IRIS_ROTATIONS * sizeof(uint16_t));
+                sent = upto;
+            }
+            producer.join();
             close(fd);
-            fprintf(stderr, sent ? "Reply sent.\n" : "Peer went away.\n");
+            if (sh.rc) {
+                fprintf(stderr, "iris_participant: batch_process: %s\n", sh.error.c_str());
+                return 1;
+            }
+            fprintf(stderr, sent_all ? "Reply sent.\n" : "Peer went away.\n");
             continue;
         }
         iris_distance_engine* engine = nullptr;

@@ -292,6 +292,75 @@ def test_batched_search_over_several_slices_equals_per_query_search(iris):
         assert mi[3] == 599_999 and mi[40] == 524_288
 
 
+def test_streamed_match_reports_rows_in_order_while_scanning(iris):
+    # the participant's producer (src/main.rs:425-434): results become available block by block
+    n = 400_000                       # three chunks of the host-output pipeline
+    qp, qm = noisy_query(5)
+    with iris.Cluster([0], n) as c:
+        c.generate(SEED, n, n_parties=2, party=0)
+        db = c.shard(0)[0]
+        ref = np.zeros((n, 31), np.uint16)
+        de = iris.DistanceEngine.from_template(qp, qm)
+        iris.match(de, None, db, 0, n, ref, None)
+        out = np.zeros((n, 31), np.uint16)
+        seen = []
+
+        def progress(b, e):
+            assert np.array_equal(out[b:e], ref[b:e])        # complete in host memory when reported
+            seen.append((b, e))
+
+        iris.match_streamed(de, None, db, 1000, n - 7, out[1000:n - 7], None, progress)
+        assert len(seen) >= 3 and seen[0][0] == 1000 and seen[-1][1] == n - 7
+        assert all(seen[i][1] == seen[i + 1][0] for i in range(len(seen) - 1))
+        assert np.array_equal(out[1000:n - 7], ref[1000:n - 7]) and not out[:1000].any() and not out[n - 7:].any()
+    with iris.Cluster(cluster_devices(iris, 3), n) as c:
+        c.generate(SEED, n, n_parties=2, party=0)
+        out = np.zeros((n, 31), np.uint16)
+        import threading
+
+        lock, covered = threading.Lock(), []
+
+        def progress2(b, e):
+            with lock:
+                covered.append((b, e))
+
+        c.match_template_streamed(qp, qm, out, progress2)
+        assert np.array_equal(out, ref)
+        covered.sort()
+        assert covered[0][0] == 0 and covered[-1][1] == n and all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+
+
+def test_scans_on_a_caller_stream_overlap_safely(iris):
+    # the reference's calling pattern (src/main.rs:427-430) on a caller-supplied stream: chunk after chunk, device outputs
+    import torch
+
+    n, chunk = 300_000, 20_000
+    q, qm = O.gen_share_rows(81, 0, 1)[0], O.gen_mask_rows(82, 0, 1)[0]
+    with iris.Database(n) as db:
+        db.generate(SEED, 0, n)
+        de, me = iris.DistanceEngine(q), iris.MasksEngine(qm)
+        ref_d = torch.zeros((n, 31), dtype=torch.int16, device="cuda")
+        ref_n = torch.zeros((n, 31), dtype=torch.int16, device="cuda")
+        db.set_overlap(False)
+        iris.match(de, me, db, 0, n, ref_d, ref_n)
+        db.synchronize()
+        db.set_overlap(True)
+        stream = torch.cuda.Stream()
+        db.set_stream(stream.cuda_stream)
+        for trial in range(3):
+            dd = torch.zeros((n, 31), dtype=torch.int16, device="cuda")
+            dn = torch.zeros((n, 31), dtype=torch.int16, device="cuda")
+            with torch.cuda.stream(stream):
+                for b in range(0, n, chunk):
+                    iris.match(de, me, db, b, b + chunk, dd[b:b + chunk], dn[b:b + chunk])
+                    if trial == 1 and b % (3 * chunk) == 0:
+                        dd[b:b + chunk].add_(0)               # foreign kernels between the scans, reading their output
+                same_d, same_n = torch.equal(dd, ref_d), torch.equal(dn, ref_n)   # stream-ordered consumers
+            stream.synchronize()
+            assert same_d and same_n
+        db.set_stream(None)
+
+
 # ---------------------------------------------------------------------------------- two or more GPUs
 def test_cluster_on_distinct_gpus_planted_in_the_last(iris):
     g = iris.device_count()

@@ -66,6 +66,7 @@ def test_participants_and_coordinator_find_the_plaintext_minimum(tmp_path):
         for p, m in queries:
             f.write(p.tobytes() + m.tobytes())                      # Template {pattern, mask}
 
+    n_gpus = mpc_iris_code_b200.device_count()
     procs, ports = [], []
     try:
         deadline = time.time() + 180
@@ -74,7 +75,9 @@ def test_participants_and_coordinator_find_the_plaintext_minimum(tmp_path):
             ports.append(port)
             procs.append(subprocess.Popen(
                 [build.PARTICIPANT_PATH, "--input", str(tmp_path / f"mpc.share-{i}"), "--bind", f"127.0.0.1:{port}",
-                 "--batch-size", "700", "--max-requests", str(len(queries))],
+                 "--batch-size", "700", "--max-requests", str(len(queries)),
+                 # participant 1 row-shards its file over three shards (distinct GPUs when the box has them)
+                 *(["--devices", ",".join(str(d % n_gpus) for d in range(3))] if i == 1 else [])],
                 stderr=subprocess.PIPE, text=True))
         for p in procs:
             _wait_listening(p, deadline)
