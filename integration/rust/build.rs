@@ -22,7 +22,11 @@ fn main() -> shadow_rs::SdResult<()> {
                 "-o",
                 &lib,
             ])
-            .args(["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan.cu", "iris_maskscan4.cu"].map(|f| format!("{src}/{f}")))
+            .args(
+                ["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan4.cu", "iris_dotbatch.cu", "iris_cluster.cu"]
+                    .map(|f| format!("{src}/{f}")),
+            )
+            .args(["-ldl", "-lpthread"])
             .status()
             .expect("nvcc not found");
         assert!(status.success(), "nvcc failed");

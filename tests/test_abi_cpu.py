@@ -182,3 +182,26 @@ def test_rust_extern_block_matches_the_header():
         assert name in c, f"{name} is bound in cuda.rs but not declared in iris_b200.h"
         want = [_C2RUST[p] for p in c[name]]
         assert rparams == want, f"{name}: cuda.rs has {rparams}, the header means {want}"
+
+
+def test_product_library_has_no_diagnostic_switches():
+    """The timing-only kernel variants and every IRIS_* environment switch live in the diagnostics build only: a stray
+    variable in a deployment must not be able to change what the product computes."""
+    import mpc_iris_code_b200 as iris
+    from mpc_iris_code_b200 import build
+
+    build.build()
+    blob = open(build.LIB_PATH, "rb").read()
+    for name in (b"IRIS_M4_VARIANT", b"IRIS_MQ_VARIANT", b"IRIS_MASKSCAN", b"IRIS_BATCHDEN", b"IRIS_BATCH_CLUSTERS"):
+        assert name not in blob, name
+    assert not iris.library_path().endswith("_diag.so") or os.environ.get("IRIS_B200_DIAG_LIB")
+    diag = open(build.build_diagnostics(), "rb").read()
+    assert b"IRIS_M4_VARIANT" in diag
+
+
+def test_rust_build_script_compiles_the_same_sources():
+    from mpc_iris_code_b200 import build
+
+    text = open(os.path.join(ROOT, "integration", "rust", "build.rs")).read()
+    listed = re.findall(r'"(iris_[a-z0-9_]+\.cu)"', text)
+    assert sorted(listed) == sorted(build.SOURCES)
