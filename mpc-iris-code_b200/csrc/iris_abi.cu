@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -80,6 +81,7 @@ extern "C" uint64_t iris_launch_count(void) { return launch_count(); }
 
 // ------------------------------------------------------------------------------------ handles
 static constexpr uint64_t kStageRows = 2048;                      // loader staging: 52 MB of shares
+static constexpr int kBatchWavePacingDefault = 1;                 // see batch_wave_pacing()
 static constexpr uint64_t kResultChunkTilesPerSm = 8;             // host-output pipeline granularity
 
 struct iris_db {
@@ -99,6 +101,7 @@ struct iris_db {
     uint64_t red_rows = 0;
     uint8_t* d_batch = nullptr;      // batched search: [Q][slice][31] distances + denominators + reduction scratch
     size_t batch_bytes = 0;
+    uint32_t* d_wave_sync = nullptr; // pacing words of the batched GEMM
     ResultPair* d_pairs = nullptr;   // per-slice result pairs of a search
     size_t pairs_cap = 0;
     // Watchdog flag: mapped page-locked HOST memory, so the code a trapping kernel leaves behind can still be read
@@ -375,6 +378,7 @@ extern "C" int iris_db_destroy(iris_db* db) {
     cudaFree(db->d_red);
     cudaFree(db->d_batch);
     cudaFree(db->d_pairs);
+    cudaFree(db->d_wave_sync);
     if (db->h_error) cudaFreeHost(db->h_error);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 2; ++k) cudaFree(db->d_res[b][k]);
@@ -1250,6 +1254,18 @@ extern "C" int iris_denominators(int device, const uint64_t* query, const uint64
 
 // ------------------------------------------------------------------------------------ batched queries (dense GEMM)
 constexpr uint32_t kBatchDistanceGroup = 8;     // queries per accumulator tile of batch_distances_kernel
+// Wave pacing of the batched GEMM (iris_batch.cu).  Diagnostics build: IRIS_BATCH_SYNC=0/1 for A/B runs.
+static bool batch_wave_pacing() {
+#ifdef IRIS_DIAGNOSTICS
+    static const int v = [] {
+        const char* e = getenv("IRIS_BATCH_SYNC");
+        return e ? atoi(e) : kBatchWavePacingDefault;
+    }();
+    return v != 0;
+#else
+    return kBatchWavePacingDefault != 0;
+#endif
+}
 #ifdef IRIS_DIAGNOSTICS
 constexpr uint32_t kBatchMaskGroup = 16;        // query masks per accumulator tile of batch_denominators_kernel
 constexpr uint32_t kBatchMaskTailLoop = 10;     // left-over masks handled by the single-query scan instead
@@ -1308,6 +1324,11 @@ extern "C" int iris_distances_batch_resident(iris_distance_engine* const* engine
             p.pair_end = (uint32_t)((row_end + 2 * kTileRows - 1) / (2 * kTileRows));
             p.num_queries = nb;
             p.error = db->d_error;
+            if (batch_wave_pacing()) {
+                if (!db->d_wave_sync) CK(cudaMalloc(reinterpret_cast<void**>(&db->d_wave_sync), 64));
+                CK(cudaMemsetAsync(db->d_wave_sync, 0, 8, db->stream));
+                p.wave_sync = db->d_wave_sync;
+            }
             CK(launch_batch_distances(p, all_s8, db->num_sms, db->stream));
         }
         if (!out_dev) {

@@ -103,7 +103,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
         const uint64_t pol_keep = ptx::policy_evict_last();
         int stage = 0;
         uint32_t phase = 0;
-        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters) {
+        uint32_t wave = 0;
+        bool pacing = p.wave_sync != nullptr && rank == 0;
+        for (uint32_t t = cluster_id; t < num_tiles; t += num_clusters, ++wave) {
+            // Wave pacing: a row tile is shared by the num_groups clusters that work on it in the same wave, but only
+            // through L2, and nothing else keeps those clusters in step -- they drift apart by whole tiles and the
+            // tile is then fetched from DRAM again.  The leaders' producers therefore start a wave together (the consumers
+            // follow within the depth of the stage ring, which also absorbs the wait).  The wait is bounded: a
+            // cluster that is not resident yet (SMs taken by another kernel) ends the pacing, never the run.
+            if (pacing) {
+                if (ptx::elect_one_sync()) {
+                    atomicAdd(p.wave_sync, 1u);                                   // this cluster has started wave `wave`
+                    // everybody that has a tile in this wave has started it
+                    const uint32_t left = num_tiles - wave * num_clusters;
+                    const uint32_t want = num_clusters * wave + (left < num_clusters ? left : num_clusters);
+                    const uint64_t t0 = ptx::globaltimer_ns();
+                    for (;;) {
+                        uint32_t seen, quit;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wave_sync) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(quit) : "l"(p.wave_sync + 1) : "memory");
+                        if (seen >= want || quit) break;
+                        if (ptx::globaltimer_ns() - t0 > 200000ull) {
+                            atomicExch(p.wave_sync + 1, 1u);                      // give up, for everybody
+                            break;
+                        }
+                        __nanosleep(100);
+                    }
+                }
+                __syncwarp();
+                uint32_t quit;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(quit) : "l"(p.wave_sync + 1) : "memory");
+                pacing = quit == 0;
+            }
             const uint32_t pair = p.pair_begin + t / num_groups;
             const uint32_t group = t % num_groups;
             const uint8_t* sh = p.shares + (size_t)(2 * pair + rank) * kShareTileBytes;

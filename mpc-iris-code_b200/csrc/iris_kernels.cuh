@@ -112,6 +112,9 @@ struct BatchParams {
     uint32_t pair_begin, pair_end;         // 256-row tile range covering [row_begin,row_end)
     uint32_t num_queries;
     int* error;
+    // Optional wave pacing (two device u32 {arrivals, gave-up}, zero before the launch; nullptr = off): the clusters that share a row tile stay
+    // in step so the tile is fetched from DRAM once and served to the other query groups from L2 (see iris_batch.cu).
+    uint32_t* wave_sync;
 };
 cudaError_t launch_batch_distances(const BatchParams& p, bool signed_queries, int num_sms, cudaStream_t stream);
 
