@@ -308,7 +308,7 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
             iris.match(de, me, db, c, e_, d_dist[c:e_], d_den[c:e_])
 
     ms_serial = _time_ms(stream, chunked, db.synchronize, warmup=1, iters=5)
-    # on the library's own stream consecutive scans with disjoint outputs overlap (programmatic dependent launch)
+    # the same on the library's own stream (host-timed)
     db.set_stream(None)
     chunked()
     db.synchronize()
@@ -320,9 +320,9 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     db.set_stream(stream.cuda_stream)
     out["fused_in_20000_row_calls_1q"] = {"ms": ms, "calls": (rows + chunk - 1) // chunk, "comparisons_per_s": rows / (ms * 1e-3),
                                           "ms_on_a_caller_stream": ms_serial,
-                                          "note": "157 tiles of 128 rows on 148 SMs per call; on the library's own stream the "
-                                                  "next call starts on the SMs the previous call's tail leaves idle, on a "
-                                                  "caller-supplied stream the calls run strictly one after the other"}
+                                          "note": "157 tiles of 128 rows on 148 SMs per call; the next call starts on the SMs the "
+                                                  "previous call's tail leaves idle (programmatic dependent launch), on the "
+                                                  "library's stream and on a caller-supplied stream alike"}
     # the coordinator's side of the same pattern: MasksEngine::batch_process on 20 000-row chunks (src/main.rs:512-515)
     def chunked_masks():
         for c in range(0, rows, chunk):
@@ -354,6 +354,32 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
                                          "algorithmic_GBps": rows * BYTES_PER_ROW_FUSED / (ms * 1e-3) / 1e9,
                                          "limb_products": 3, "sm_mhz": _NVML["last_mhz"]}
     du.close()
+    # the reference's LITERAL signature: batch_process(out, db) with `db` a HOST slice (src/lib.rs:42-52) -- rows are
+    # uploaded, re-tiled and scanned in a double-buffered pipeline; PCIe-bound by construction, so the yardstick is a
+    # bare pinned host->device copy of the same bytes
+    hs_rows = 100_000
+    h_rows = torch.empty((hs_rows, 12800), dtype=torch.int16).pin_memory()
+    h_rows.random_(-32768, 32767)
+    h_out = torch.empty((hs_rows, 31), dtype=torch.int16).pin_memory()
+    d_tmp = torch.empty((hs_rows, 12800), dtype=torch.int16, device="cuda")
+    rows_np, out_np = h_rows.numpy().view(np.uint16), h_out.numpy().view(np.uint16)
+    de.batch_process(out_np, rows_np)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        de.batch_process(out_np, rows_np)
+    hs = (time.perf_counter() - t0) / 3
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d_tmp.copy_(h_rows, non_blocking=True)
+        torch.cuda.synchronize()
+    bare = (time.perf_counter() - t0) / 3
+    out["host_slice_batch_process_1q"] = {"rows": hs_rows, "ms": hs * 1e3, "comparisons_per_s": hs_rows / hs,
+                                          "host_to_device_GBps": hs_rows * 25600 / hs / 1e9,
+                                          "bare_h2d_GBps": hs_rows * 25600 / bare / 1e9,
+                                          "frac_of_bare_h2d": bare / hs,
+                                          "note": "DistanceEngine::batch_process(out, db) with db and out in (pinned) host memory"}
+    del h_rows, h_out, d_tmp
     # int8 library GEMM on this box: the measured tensor-core denominator
     a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")
     b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device="cuda")

@@ -113,6 +113,7 @@ struct iris_db {
     static constexpr int kChain = 6;
     uintptr_t chain_lo[kChain][2] = {}, chain_hi[kChain][2] = {};
     int chain_len = 0;
+    bool chain_all_wide = true;      // every scan of the current chain has at least num_sms / 2 CTAs
     bool overlap = true;             // consecutive device-output scans of this shard may overlap (iris_db_set_overlap)
 };
 
@@ -733,12 +734,28 @@ static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* m
         const size_t bytes = (size_t)(row_end - row_begin) * kOutRowBytes;
         const uintptr_t lo[2] = {reinterpret_cast<uintptr_t>(dist_out), reinterpret_cast<uintptr_t>(den_out)};
         const uintptr_t hi[2] = {dist_out ? lo[0] + bytes : 0, den_out ? lo[1] + bytes : 0};
+        // A scan with at least num_sms / 2 CTAs (one CTA per SM) can start only when its predecessor is fully resident,
+        // i.e. when at most one older scan still holds SMs: three scans in flight at the very most, so for such scans
+        // the last kChain ranges are a sliding window and the chain never has to be drained.
+        const uint32_t grid_ctas = std::min<uint32_t>(p.tile_end - p.tile_begin, (uint32_t)db->num_sms);
+        if (db->chain_len == iris_db::kChain && db->chain_all_wide && grid_ctas >= (uint32_t)db->num_sms / 2) {
+            for (int i = 1; i < iris_db::kChain; ++i)
+                for (int a = 0; a < 2; ++a) {
+                    db->chain_lo[i - 1][a] = db->chain_lo[i][a];
+                    db->chain_hi[i - 1][a] = db->chain_hi[i][a];
+                }
+            --db->chain_len;
+        }
         bool chain = db->overlap && !raw_dev && db->chain_len < iris_db::kChain;
         for (int i = 0; chain && i < db->chain_len; ++i)
             for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 2; ++b)
                     if (lo[a] < db->chain_hi[i][b] && db->chain_lo[i][b] < hi[a]) chain = false;
-        if (!chain) db->chain_len = 0;          // an ordinary launch waits for everything before it
+        if (!chain) {                           // an ordinary launch waits for everything before it
+            db->chain_len = 0;
+            db->chain_all_wide = true;
+        }
+        if (grid_ctas < (uint32_t)db->num_sms / 2) db->chain_all_wide = false;
         p.pdl = chain && db->chain_len > 0;
         for (int a = 0; a < 2; ++a) {
             db->chain_lo[db->chain_len][a] = lo[a];

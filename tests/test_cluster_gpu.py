@@ -253,6 +253,36 @@ def test_cluster_search_ties_go_to_the_lowest_row(iris):
         assert mi[0] == -1 and md[0] == np.inf
 
 
+def test_cluster_edge_shapes(iris):
+    # fewer rows than shards (empty blocks), an empty database, more queries than one pass holds, zero queries
+    with iris.Cluster(cluster_devices(iris, 3), 900) as c:
+        c.generate(SEED, 2, n_parties=1)                      # blocks of 1, 1 and 0 rows
+        assert [c.shard(i)[3] - c.shard(i)[2] for i in range(3)] == [1, 1, 0]
+        qp, qm = noisy_query(1, flips=500, rotation=0)
+        md, mi = c.search(np.concatenate([qp, qm])[None, :].copy())
+        p1, m1 = synthetic_template(1)
+        assert (md[0], mi[0]) == (O.template_distance(qp, qm, p1, m1), 1)
+        out = np.zeros((2, 31), np.uint16)
+        c.match_template(qp, qm, out)
+        assert np.array_equal(out, O.distance_batch(O.encode(qp, qm), O.gen_party_share_rows(SEED, 0, 1, 0, 2)))
+        c.generate(SEED, 0, n_parties=1)                      # nothing at all
+        md, mi = c.search(np.concatenate([qp, qm])[None, :].copy())
+        assert mi[0] == -1 and md[0] == np.inf
+        md, mi = c.search(np.zeros((5, 400), np.uint64))
+        assert (mi == -1).all() and np.isinf(md).all()
+        c.match_template(qp, qm, np.zeros((0, 31), np.uint16))
+        md, mi = c.search(np.zeros((0, 400), np.uint64))
+        assert len(md) == 0
+        n = 700
+        c.generate(SEED, n, n_parties=1)
+        tq = np.random.default_rng(21).integers(0, 2**64, size=(70, 400), dtype=np.uint64)   # 64 + 6 queries
+        tq[66, :200], tq[66, 200:] = noisy_query(n - 1)
+        md, mi = c.search(tq)
+        assert mi[66] == n - 1
+        for k in (0, 63, 64, 69):
+            assert (md[k], mi[k]) == plaintext_min(tq[k, :200].copy(), tq[k, 200:].copy(), range(n))
+
+
 def test_cluster_loads_the_reference_files(iris, tmp_path):
     n = 1000
     shares, masks = O.gen_share_rows(SEED, 0, n, threads=8), O.gen_mask_rows(SEED, 0, n, threads=8)

@@ -2,7 +2,9 @@
 change which falls off the fast path -- a kernel variant switch left on, a serialising sync, a lost overlap, a lost
 tail overlap of the chunked calls -- fails a test instead of only moving a bench number.  Times are CUDA-event means over
 back-to-back launches after a warm-up; each figure is the best of three attempts (a neighbour on a shared box must not
-fail the suite) and the SM clock seen while measuring is part of the failure message."""
+fail the suite).  The HBM-bound scans are held to 1.3x outright; the tensor-bound batched kernels follow the SM clock,
+which the 1 kW cap moves between 1.2 and 1.97 GHz depending on what ran before, so their allowance is 1.3x scaled by
+max clock / the clock sampled while measuring (and that clock is part of the failure message)."""
 import numpy as np
 import pytest
 
@@ -33,19 +35,31 @@ def ctx():
 _CLOCK = {"mhz": None}
 
 
-def _sm_mhz():
+def _sm_mhz(kind="now"):
     try:
         import pynvml
 
         pynvml.nvmlInit()
-        return pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByIndex(0), pynvml.NVML_CLOCK_SM)
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        if kind == "max":
+            return pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        return pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
     except Exception:  # noqa: BLE001
         return None
 
 
+def _clock_allowance():
+    """max clock / sampled clock (>= 1): how much slower a clock-bound kernel may legitimately be right now."""
+    now, top = _CLOCK["mhz"], _sm_mhz("max")
+    return max(1.0, top / now) if now and top else 1.0
+
+
 def _mean_ms(torch, stream, db, fn, warm, iters, attempts=3):
+    import time
+
     best = float("inf")
     for _ in range(attempts):
+        time.sleep(0.5)                    # let the power-averaging window recover between attempts
         for _ in range(warm):
             fn()
         db.synchronize()
@@ -54,9 +68,11 @@ def _mean_ms(torch, stream, db, fn, warm, iters, attempts=3):
         for _ in range(iters):
             fn()
         e.record(stream)
-        _CLOCK["mhz"] = _sm_mhz()          # sampled while the timed launches are running
+        mhz = _sm_mhz()                    # sampled while the timed launches are running
         db.synchronize()
-        best = min(best, s.elapsed_time(e) / iters)
+        ms = s.elapsed_time(e) / iters
+        if ms < best:
+            best, _CLOCK["mhz"] = ms, mhz
     return best
 
 
@@ -68,16 +84,17 @@ def test_single_query_scans_stay_near_the_hbm_rate(ctx):
     den = torch.empty((rows, 31), dtype=torch.int16, device="cuda")
     fused = _mean_ms(torch, stream, db, lambda: iris.match(de, me, db, 0, rows, dist, den), 3, 10)
     dists = _mean_ms(torch, stream, db, lambda: iris.match(de, None, db, 0, rows, dist, None), 3, 10)
-    masks = _mean_ms(torch, stream, db, lambda: iris.match(None, me, db, 0, rows, None, den), 50, 100)
     clk = _CLOCK["mhz"]
     assert fused < 5.1, f"fused scan {fused:.2f} ms per 1 M rows (measured: 3.9), SM {clk} MHz"
     assert dists < 4.7, f"distances-only scan {dists:.2f} ms per 1 M rows (measured: 3.6), SM {clk} MHz"
-    assert masks < 0.39, f"denominators-only scan {masks:.3f} ms per 1 M rows (measured: 0.28-0.30), SM {clk} MHz"
+    masks = _mean_ms(torch, stream, db, lambda: iris.match(None, me, db, 0, rows, None, den), 50, 100)
+    lim, clk = 1.3 * 0.29 * _clock_allowance(), _CLOCK["mhz"]    # this one follows the SM clock
+    assert masks < lim, f"denominators-only scan {masks:.3f} ms per 1 M rows (0.28-0.30 at full clock; limit {lim:.3f}), SM {clk} MHz"
 
 
 def test_chunked_calls_keep_their_tail_overlap(ctx):
-    # the reference's 20 000-row calls (src/main.rs:427-430) on a caller-supplied stream: 4.5 ms per 1 M rows with the
-    # tails overlapped, 7.7 ms strictly serial
+    # the reference's 20 000-row calls (src/main.rs:427-430) on a caller-supplied stream: 4.0 ms per 1 M rows with the
+    # tails overlapped (= one full-range call), 7.7 ms strictly serial
     iris, torch, stream, db, rows, tmpl = ctx
     de = iris.DistanceEngine.from_template(tmpl[1, :200].copy(), tmpl[1, 200:].copy())
     me = iris.MasksEngine(tmpl[1, 200:].copy())
@@ -89,7 +106,7 @@ def test_chunked_calls_keep_their_tail_overlap(ctx):
             iris.match(de, me, db, b, b + 20_000, dist[b:b + 20_000], den[b:b + 20_000])
 
     ms = _mean_ms(torch, stream, db, chunked, 1, 3)
-    assert ms < 5.9, f"fused scan in 20 000-row calls {ms:.2f} ms per 1 M rows (measured: 4.5), SM {_CLOCK['mhz']} MHz"
+    assert ms < 5.2, f"fused scan in 20 000-row calls {ms:.2f} ms per 1 M rows (measured: 4.0), SM {_CLOCK['mhz']} MHz"
 
 
 def test_batched_paths_stay_on_the_tensor_kernels(ctx):
@@ -98,7 +115,8 @@ def test_batched_paths_stay_on_the_tensor_kernels(ctx):
     des, mes = iris.engines_from_templates(tmpl)
     out = torch.empty((16, n, 31), dtype=torch.int16, device="cuda")
     dists = _mean_ms(torch, stream, db, lambda: iris.distances_batch(des, db, 0, n, out), 2, 5)
+    lim, clk = 1.3 * 1.6 * _clock_allowance(), _CLOCK["mhz"]
+    assert dists < lim, f"16 queries x 200 k rows, distances: {dists:.2f} ms (1.6 at full clock; limit {lim:.2f}), SM {clk} MHz"
     masks = _mean_ms(torch, stream, db, lambda: iris.denominators_batch(mes, db, 0, n, out), 2, 5)
-    clk = _CLOCK["mhz"]
-    assert dists < 2.5, f"16 queries x 200 k rows, distances: {dists:.2f} ms (measured: 1.9), SM {clk} MHz"
-    assert masks < 0.6, f"16 masks x 200 k rows, denominators: {masks:.2f} ms (measured: 0.45), SM {clk} MHz"
+    lim, clk = 1.3 * 0.45 * _clock_allowance(), _CLOCK["mhz"]
+    assert masks < lim, f"16 masks x 200 k rows, denominators: {masks:.2f} ms (0.45 at full clock; limit {lim:.2f}), SM {clk} MHz"
