@@ -681,6 +681,24 @@ def run_b200(args):
     search_s = timed_host_loop(search_step, e2e_steps)
     sampler.active.clear()
     sampler.stop_flag.set()
+    # the kernel behind that call, device-timed on its own: the fused scan in SEARCH MODE (decode + running minimum in
+    # the epilogue, no per-row results written), plus the 148-entry final reduction
+    e1, e2 = iris.DistanceEngine.from_template(s_p, s_m, device=local_rank), iris.MasksEngine(s_m, device=local_rank)
+    pair = torch.zeros(2, dtype=torch.int64, device="cuda")
+    db.set_stream(stream.cuda_stream)
+    for _ in range(3):
+        iris.match_min_async(e1, e2, db, 0, rows, pair, index_base=row0)
+    db.synchronize()
+    sev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    sev[0].record(stream)
+    for _ in range(e2e_steps):
+        iris.match_min_async(e1, e2, db, 0, rows, pair, index_base=row0)
+    sev[1].record(stream)
+    db.synchronize()
+    search_kernel_ms = max_over_ranks(sev[0].elapsed_time(sev[1]) / e2e_steps)
+    db.set_stream(None)
+    e1.close()
+    e2.close()
     e2e_value = n_total * e2e_steps / search_s
     search_ok = bool(found["i"] == target and found["d"] == expected)
 
@@ -726,6 +744,13 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": rows * BYTES_PER_ROW_FUSED, "launch_ms": per_launch_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3200, "d2h_bytes_per_step": 16, "steps": e2e_steps,
                 "ms_per_query": search_s / e2e_steps * 1e3,
+                "kernel": "scan_kernel<shares,masks,search>: the fused scan with decode_distance + running min/argmin in its "
+                          "epilogue; no per-row results are written, which is why this path can be FASTER than `value` "
+                          "(whose kernel stores 124 B per row)",
+                "kernel_only_ms": search_kernel_ms,
+                "kernel_roofline": {"achieved_GBps": rows * 27200 / (search_kernel_ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": rows * 27200 / (search_kernel_ms * 1e-3) / 1e9 / hbm_peak_gbs()[0],
+                                    "algorithmic_bytes_per_launch": rows * 27200},
                 "path": "iris_cluster_search (C ABI): wire Template from pinned host memory -> encode + both engines on the "
                         "device -> fused scan -> decode_distance + min/argmin on the device -> "
                         + ("all-gather of the shards' (min, argmin) pairs over NCCL -> " if world > 1 else "")

@@ -25,6 +25,7 @@ from .api import (  # noqa: F401
     combine_min,
     combine_min_batch,
     match_min,
+    match_min_async,
     denominators,
     denominators_batch,
     device_count,

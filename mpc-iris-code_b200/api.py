@@ -51,6 +51,8 @@ def lib():
     from . import build as _build
 
     path = _build.build_diagnostics() if _diagnostics_requested() else _build.build()
+    if os.environ.get("IRIS_B200_LIB"):          # an explicitly built A/B library (tests/diagnostics only)
+        path = os.environ["IRIS_B200_LIB"]
     L = ctypes.CDLL(path)
     vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
     pp = ctypes.POINTER(ctypes.c_void_p)
@@ -536,6 +538,15 @@ def match_min(distance_engine: DistanceEngine, masks_engine: MasksEngine, db: Da
     _check(lib().iris_match_min_resident(distance_engine._h, masks_engine._h, db._h, row_begin, row_end, index_base,
                                          ctypes.byref(md), ctypes.byref(mi)))
     return md.value, (-1 if mi.value == 2**64 - 1 else mi.value)
+
+
+def match_min_async(distance_engine: DistanceEngine, masks_engine: MasksEngine, db: Database, row_begin: int, row_end: int,
+                    result, index_base: int = 0) -> None:
+    """The asynchronous form: the {f64 min, u64 row} pair (16 bytes) is written to `result` (a torch CUDA tensor of
+    two int64 / uint64 elements, or any device / mapped address) in stream order; no host synchronisation."""
+    ptr = result.data_ptr() if _is_torch(result) else int(result)
+    _check(lib().iris_match_min_resident_async(distance_engine._h, masks_engine._h, db._h, row_begin, row_end, index_base,
+                                               ctypes.c_void_p(ptr)))
 
 
 def raw_accumulators(distance_engine, masks_engine, db: Database, row_begin: int, row_end: int) -> np.ndarray:

@@ -1657,32 +1657,42 @@ extern "C" int iris_match_min_resident_async(iris_distance_engine* de, iris_mask
                                              uint64_t row_end, uint64_t index_base, void* result) {
     if (!de || !me || !db || !result) return fail(IRIS_ERR_INVALID, "NULL argument");
     if (row_end < row_begin) return fail(IRIS_ERR_INVALID, "row_begin > row_end");
+    if (de->device != db->device || me->device != db->device) return fail(IRIS_ERR_INVALID, "engine and shard live on different devices");
+    if (!db->d_shares || !db->d_masks) return fail(IRIS_ERR_STATE, "a search needs shares and masks in the shard");
+    if (row_end > db->n_shares || row_end > db->n_masks) return fail(IRIS_ERR_INVALID, "row_end beyond the loaded rows");
     DeviceGuard g(db->device);
-    const uint64_t n = row_end - row_begin;
-    if (db->red_rows < n || !db->d_red) {
-        CK(cudaStreamSynchronize(db->stream));           // an earlier asynchronous search may still use the buffer
-        cudaFree(db->d_red);
-        db->d_red = nullptr;
-        db->red_rows = 0;
-        const size_t row_bytes = (n * kOutRowBytes + 63) / 64 * 64;
-        CK(cudaMalloc(&db->d_red, 2 * row_bytes + combine_scratch_bytes(n) + 64));
-        db->red_rows = n;
+    // one (min, row) pair per CTA of the scan: the scan's epilogue decodes and reduces (search mode), nothing per row
+    // is written or read back
+    if (!db->d_red) {
+        CK(cudaMalloc(&db->d_red, 2 * 1024 * sizeof(double)));
+        db->red_rows = 1024;
     }
-    const size_t row_bytes = (db->red_rows * kOutRowBytes + 63) / 64 * 64;
-    uint16_t* d_dist = reinterpret_cast<uint16_t*>(db->d_red);
-    uint16_t* d_den = reinterpret_cast<uint16_t*>(db->d_red + row_bytes);
-    uint8_t* scratch = db->d_red + 2 * row_bytes;
-    if (n) {
-        int rc = scan_core(db, de, me, row_begin, row_end, d_dist, d_den, nullptr);
-        if (rc) return rc;
-    }
-    CombineParams p{};
-    p.shares[0] = d_dist;
-    p.parties = 1;
-    p.denominators = d_den;
-    p.n = n;
-    p.index_base = index_base + row_begin;
-    CK(launch_combine_min(p, scratch, result, db->stream));
+    int rc = engine_resolve(de);
+    if (!rc) rc = engine_begin_use(de->slot, de->use, db);
+    if (!rc) rc = engine_begin_use(me->slot, me->use, db);
+    if (rc) return rc;
+    ScanParams p{};
+    p.shares = db->d_shares;
+    p.masks = db->d_masks;
+    p.qd = de->d_qd;
+    p.qm = me->d_qm;
+    p.error = db->d_error;
+    p.signed_query = de->fits_s8;
+    p.row_begin = row_begin;
+    p.row_end = row_end;
+    p.tile_begin = (uint32_t)(row_begin / kTileRows);
+    p.tile_end = (uint32_t)((row_end + kTileRows - 1) / kTileRows);
+    p.red_min = reinterpret_cast<double*>(db->d_red);
+    p.red_idx = reinterpret_cast<unsigned long long*>(db->d_red + 1024 * sizeof(double));
+    p.index_base = index_base;
+    const uint32_t blocks = row_end > row_begin ? scan_grid(p, db->num_sms) : 0;
+    if (blocks > 1024) return fail(IRIS_ERR_STATE, "scan grid of %u CTAs", blocks);
+    // an ordinary launch: it starts when every earlier scan of this shard has completed (the per-CTA pairs are reused
+    // from search to search), and it ends the chain of overlapping scans
+    db->chain_len = 0;
+    db->chain_all_wide = true;
+    if (blocks) CK(launch_scan(p, db->num_sms, db->stream));
+    CK(launch_final_min(p.red_min, p.red_idx, blocks, static_cast<ResultPair*>(result), db->stream));
     return IRIS_OK;
 }
 

@@ -6,6 +6,26 @@
 
 namespace iris {
 
+// Result stores are streaming stores (st.global.cs): the rows are written once and read much later by another kernel or
+// a copy engine, and plain stores cost the HBM-bound scan 2.4 % (3.91 -> 3.81 ms per 1 M rows fused; tests/diagnostics/
+// store_mode_bench.py).  IRIS_STORE_MODE (compile-time, A/B builds only): 0 = plain st.global, 1 = st.global.cs,
+// 2 = st.global with an L2 evict_first policy (same time as 1).
+#ifndef IRIS_STORE_MODE
+#define IRIS_STORE_MODE 1
+#endif
+__device__ __forceinline__ void store_out16(uint8_t* g, const uint4& v) {
+#if IRIS_STORE_MODE == 1
+    __stcs(reinterpret_cast<uint4*>(g), v);
+#elif IRIS_STORE_MODE == 2
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+#else
+    *reinterpret_cast<uint4*>(g) = v;
+#endif
+}
+
 // Copies bytes [b0,b1) (offsets inside `stage`, both even) to gbase + offset, where gbase is 16-byte aligned and
 // congruent with `stage`: 16-byte body, 2-byte head / tail.  Executed by the 128 epilogue threads (tid 0..127).
 __device__ __forceinline__ void copy_out_rows(const uint8_t* stage, uint8_t* gbase, int b0, int b1, int tid) {
@@ -19,7 +39,7 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* stage, uint8_t* gba
     for (int b = b0 + 2 * tid; b < body0; b += 2 * 128)
         *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
     for (int b = body0 + 16 * tid; b < body1; b += 16 * 128)
-        *reinterpret_cast<uint4*>(gbase + b) = *reinterpret_cast<const uint4*>(stage + b);
+        store_out16(gbase + b, *reinterpret_cast<const uint4*>(stage + b));
     for (int b = body1 + 2 * tid; b < b1; b += 2 * 128)
         *reinterpret_cast<uint16_t*>(gbase + b) = *reinterpret_cast<const uint16_t*>(stage + b);
 }

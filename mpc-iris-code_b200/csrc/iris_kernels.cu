@@ -64,8 +64,10 @@ constexpr uint32_t kTmemCols = 256;   // 2 accumulator buffers x 128 columns
 enum WatchdogCode { kWdProducer = 101, kWdMmaFull = 102, kWdMmaExp = 103, kWdMmaTmem = 104, kWdExpander = 105, kWdEpilogue = 106 };
 
 
-template <bool S, bool M, bool SQ>
+// R (search mode, fused scan only): decode + running minimum in the epilogue instead of per-row results.
+template <bool S, bool M, bool SQ, bool R = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams p) {
+    static_assert(!R || (S && M), "search mode needs distances and denominators");
     using Cfg = ScanCfg<S, M, SQ>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -214,6 +216,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
         // ------------------------------------------------------------------ epilogue (warps 0..3)
         const int row = threadIdx.x;   // 0..127 == TMEM lane
         uint32_t it = 0;
+        // search mode: this thread's best row so far as an exact fraction (best_d = 0: none yet) -- see
+        // combine_decode_kernel (iris_reduce.cu) for why comparing fractions equals comparing the f64 quotients
+        uint32_t best_n = 0, best_d = 0;
+        unsigned long long best_row = ~0ull;
         for (uint32_t tile = tile0; tile < p.tile_end; tile += tile_step, ++it) {
             const uint32_t buf = it & 1u;
             ptx::mbar_wait(tfull_bar(buf), (it >> 1) & 1u, p.error, kWdEpilogue);
@@ -224,6 +230,41 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
             const int64_t trow0 = (int64_t)tile * kTileRows;
             int r0 = (int)max((int64_t)0, (int64_t)p.row_begin - trow0);
             int r1 = (int)min((int64_t)kTileRows, (int64_t)p.row_end - trow0);
+            if (R) {
+                uint32_t a[32], b[32], c2[32], m[32];
+                ptx::tmem_ld32(taddr + 0, a);
+                if (SQ) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) b[j] = 0;
+                } else {
+                    ptx::tmem_ld32(taddr + 32, b);
+                }
+                ptx::tmem_ld32(taddr + 64, c2);
+                ptx::tmem_ld32(taddr + 96, m);
+                ptx::tmem_wait_ld();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(tempty_bar(buf));             // the accumulators are in registers
+                if (row >= r0 && row < r1) {
+                    uint32_t bn = 0, bd = 0;                   // this row: min over the rotations (src/lib.rs:97-107)
+#pragma unroll
+                    for (int j = 0; j < IRIS_ROTATIONS; ++j) {
+                        const uint32_t dist = (a[j] + ((b[j] + c2[j]) << 8)) & 0xFFFFu;
+                        const uint32_t den = (m[j] >> 7) & 0xFFFFu;
+                        const uint32_t num = ((den - dist) & 0xFFFFu) >> 1;
+                        if (den != 0 && (bd == 0 || num * bd < bn * den)) {
+                            bn = num;
+                            bd = den;
+                        }
+                    }
+                    // strict `<` against the running minimum (src/main.rs:617): rows come in ascending order
+                    if (bd != 0 && (best_d == 0 || (uint64_t)bn * best_d < (uint64_t)best_n * bd)) {
+                        best_n = bn;
+                        best_d = bd;
+                        best_row = p.index_base + (uint64_t)(trow0 + row);
+                    }
+                }
+                continue;
+            }
             // byte offset (possibly negative) of tile row 0 in the packed output
             const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
 
@@ -280,6 +321,35 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
             }
             ptx::named_bar_sync(1, 128);
         }
+        if (R) {
+            // CTA minimum: one division per thread, warp shuffles, then the four epilogue warps through shared memory
+            double v = best_d ? (double)best_n / (double)best_d : __longlong_as_double(0x7FF0000000000000ll);
+            unsigned long long i = best_row;
+            for (int o = 16; o; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const unsigned long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+                if (ov < v || (ov == v && oi < i)) {
+                    v = ov;
+                    i = oi;
+                }
+            }
+            double* sv = reinterpret_cast<double*>(out_stage_ptr);
+            unsigned long long* si = reinterpret_cast<unsigned long long*>(out_stage_ptr + 64);
+            if ((threadIdx.x & 31) == 0) {
+                sv[warp] = v;
+                si[warp] = i;
+            }
+            ptx::named_bar_sync(1, 128);
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < 4; ++w)
+                    if (sv[w] < v || (sv[w] == v && si[w] < i)) {
+                        v = sv[w];
+                        i = si[w];
+                    }
+                p.red_min[blockIdx.x] = v;
+                p.red_idx[blockIdx.x] = i;
+            }
+        }
     }
 
     ptx::tc_fence_before();
@@ -288,7 +358,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanParams 
     ptx::pdl_wait();                            // complete in stream order
 }
 
-template <bool S, bool M, bool SQ>
+template <bool S, bool M, bool SQ, bool R = false>
 static cudaError_t launch_scan_t(const ScanParams& p, int num_sms, cudaStream_t stream) {
     using Cfg = ScanCfg<S, M, SQ>;
     static std::atomic<bool> configured[64];    // per device: opt-in shared memory size set
@@ -296,7 +366,7 @@ static cudaError_t launch_scan_t(const ScanParams& p, int num_sms, cudaStream_t 
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(scan_kernel<S, M, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        e = cudaFuncSetAttribute(scan_kernel<S, M, SQ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
         if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
@@ -315,15 +385,25 @@ static cudaError_t launch_scan_t(const ScanParams& p, int num_sms, cudaStream_t 
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
         count_launch();
-        return cudaLaunchKernelEx(&cfg, scan_kernel<S, M, SQ>, p);
+        return cudaLaunchKernelEx(&cfg, scan_kernel<S, M, SQ, R>, p);
     }
-    scan_kernel<S, M, SQ><<<grid, kScanThreads, Cfg::kSmemBytes, stream>>>(p);
+    scan_kernel<S, M, SQ, R><<<grid, kScanThreads, Cfg::kSmemBytes, stream>>>(p);
     count_launch();
     return cudaGetLastError();
 }
 
+uint32_t scan_grid(const ScanParams& p, int num_sms) {
+    const uint32_t tiles = p.tile_end - p.tile_begin;
+    return tiles < (uint32_t)num_sms ? tiles : (uint32_t)num_sms;
+}
+
 cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream) {
     const bool s = p.shares != nullptr, m = p.masks != nullptr;
+    if (p.red_min || p.red_idx) {
+        if (!s || !m || !p.red_min || !p.red_idx || p.raw_out) return cudaErrorInvalidValue;
+        return p.signed_query ? launch_scan_t<true, true, true, true>(p, num_sms, stream)
+                              : launch_scan_t<true, true, false, true>(p, num_sms, stream);
+    }
     if (s && m) return p.signed_query ? launch_scan_t<true, true, true>(p, num_sms, stream)
                                       : launch_scan_t<true, true, false>(p, num_sms, stream);
     if (s) return p.signed_query ? launch_scan_t<true, false, true>(p, num_sms, stream)

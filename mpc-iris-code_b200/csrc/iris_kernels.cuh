@@ -23,7 +23,15 @@ struct ScanParams {
     int* error;              // device int, set by the watchdog
     bool signed_query;       // query elements are sign-extended bytes: two-product path (q_lo plane as s8)
     bool pdl;                // launch with programmatic stream serialization (may overlap the previous scan's tail)
+    // Search mode (fused scan only, both red_* set): nothing is stored per row.  The epilogue decodes each row
+    // (src/lib.rs:97-107) and keeps a running (min distance, row) per CTA (src/main.rs:611-621); CTA b writes its pair to
+    // red_min[b] / red_idx[b] (gridDim.x entries, reduced afterwards by launch_final_min).  Row ids = index_base + row.
+    double* red_min;
+    unsigned long long* red_idx;
+    uint64_t index_base;
 };
+// CTAs a scan launch uses (= entries of red_min / red_idx a search-mode launch writes).
+uint32_t scan_grid(const ScanParams& p, int num_sms);
 
 // Launches the persistent tcgen05 scan.  Mode is derived from which of shares/masks is non-null.
 cudaError_t launch_scan(const ScanParams& p, int num_sms, cudaStream_t stream);
@@ -147,6 +155,9 @@ struct ResultPair {                        // what a search returns per query: 1
 };
 size_t combine_scratch_bytes(uint64_t n);  // per query
 cudaError_t launch_combine_min(const CombineParams& p, void* scratch, void* result, cudaStream_t stream, uint32_t num_queries = 1);
+// result pair = best of n per-block (min, index) entries (lowest index on ties); the second half of launch_combine_min
+cudaError_t launch_final_min(const double* block_min, const unsigned long long* block_idx, uint32_t n, ResultPair* result,
+                             cudaStream_t stream);
 // out[q] = best over s < n_sets of in[s * stride + q] (lowest index on ties; ~0 indices ignored)
 cudaError_t launch_merge_pairs(const ResultPair* in, uint32_t n_sets, uint32_t stride, uint32_t n_queries, ResultPair* out,
                                cudaStream_t stream);

@@ -75,13 +75,24 @@ __global__ void __launch_bounds__(kReduceThreads) combine_decode_kernel(const Co
     double best = CUDART_INF;
     unsigned long long idx = ~0ull;
     if (row < p.n) {
+        // decode_distance (src/lib.rs:97-107) folds f64::min over the 31 quotients num / den.  f64 division is the
+        // slowest thing this GPU does, so the minimum is found on the exact fractions (num_a * den_b < num_b * den_a,
+        // products below 2^32) and only the winner is divided.  Same result bit for bit: two different fractions with
+        // denominators below 2^16 are more than 2^-32 apart and correctly rounded division is monotonic, so the
+        // smallest fraction is the smallest quotient.  den = 0 gives NaN (num = 0: dropped by f64::min) or +inf
+        // (never below the fold's initial INFINITY), so those rotations cannot win either way.
+        uint32_t bn = 0, bd = 0;                               // bd = 0: no finite quotient yet
 #pragma unroll
         for (int j = 0; j < IRIS_ROTATIONS; ++j) {
             const uint16_t s = s_num[threadIdx.x * IRIS_ROTATIONS + j];
-            const uint16_t d = s_den[threadIdx.x * IRIS_ROTATIONS + j];
-            const uint16_t num = (uint16_t)((uint16_t)(d - s) >> 1);
-            best = fmin(best, (double)num / (double)d);      // fmin drops a NaN operand like f64::min
+            const uint32_t d = s_den[threadIdx.x * IRIS_ROTATIONS + j];
+            const uint32_t num = (uint16_t)((uint16_t)(d - s) >> 1);
+            if (d != 0 && (bd == 0 || num * bd < bn * d)) {
+                bn = num;
+                bd = d;
+            }
         }
+        if (bd) best = (double)bn / (double)bd;
         idx = p.index_base + row;
         if (p.distances_out) p.distances_out[(size_t)blockIdx.y * p.n + row] = best;
     }
@@ -164,6 +175,13 @@ cudaError_t launch_combine_min(const CombineParams& p, void* scratch, void* resu
         count_launch_external();
     }
     final_min_kernel<<<num_queries, kReduceThreads, 0, stream>>>(bmin, bidx, blocks, static_cast<ResultPair*>(result));
+    count_launch_external();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_final_min(const double* block_min, const unsigned long long* block_idx, uint32_t n, ResultPair* result,
+                             cudaStream_t stream) {
+    final_min_kernel<<<1, kReduceThreads, 0, stream>>>(block_min, block_idx, n, result);
     count_launch_external();
     return cudaGetLastError();
 }

@@ -462,6 +462,29 @@ def test_combine_min_matches_reference_coordinator(iris, small):
     assert iris.combine_min([z], z) == (np.inf, -1)
 
 
+def test_decode_on_arbitrary_u16_pairs_is_bit_identical(iris):
+    """decode_distance (src/lib.rs:97-107) on the device picks the smallest FRACTION exactly and divides once; the
+    reference divides 31 times and folds f64::min.  Same bits for any u16 inputs: uniform pairs, denominators of zero
+    (NaN / +inf rotations), near-equal fractions with large denominators, and rows where every rotation is NaN."""
+    r = np.random.default_rng(2026)
+    n = 200_000
+    dist = r.integers(0, 2**16, size=(n, 31), dtype=np.uint16)
+    den = r.integers(0, 2**16, size=(n, 31), dtype=np.uint16)
+    den[r.random((n, 31)) < 0.05] = 0                                   # scattered zero denominators
+    den[:50] = 0                                                         # rows with no finite quotient at all
+    dist[:25] = 0                                                        # ... 0/0 = NaN everywhere -> +inf
+    big = r.integers(65000, 65536, size=(1000, 31), dtype=np.uint16)    # neighbouring fractions near 1/2
+    den[1000:2000] = big
+    dist[1000:2000] = (big.astype(np.int64) - 2 * (big.astype(np.int64) // 2 - r.integers(0, 3, size=big.shape))).astype(np.uint16)
+    den[3000:3100] = 1                                                   # quotients far above 1
+    md, mi, got = iris.combine_min([dist], den, want_distances=True)
+    exp = np.array([O.decode_distance(dist[i], den[i]) for i in range(0, n, 7)])
+    assert np.array_equal(got[::7], exp)
+    exp_head = np.array([O.decode_distance(dist[i], den[i]) for i in range(3200)])
+    assert np.array_equal(got[:3200], exp_head) and np.isinf(got[:50]).all()
+    assert (md, mi) == O.combine_min(dist[None], den)
+
+
 def test_match_min_fused_scan_and_reduction(iris):
     n = 3000
     qp, qm = O.gen_mask_rows(71, 0, 1)[0], O.gen_mask_rows(71, 1, 1)[0]
