@@ -354,6 +354,41 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
                                          "algorithmic_GBps": rows * BYTES_PER_ROW_FUSED / (ms * 1e-3) / 1e9,
                                          "limb_products": 3, "sm_mhz": _NVML["last_mhz"]}
     du.close()
+    # BASELINE configs[0] on the GPU: the reference's criterion grids (src/arch/mod.rs:22-72) -- dot_u16 on every pair of
+    # 31 INDEPENDENT uniform vectors x 100 000 rows, dot_bool on 31 x 1 000 and 1 x 100 000 -- through the arch-level
+    # entry points (iris_dot_*_batch_resident: the 31 vectors take the slots of the 31 rotations); Elements = a x b
+    grid = {}
+    try:
+        n_b = 100_000
+        gdb = iris.Database(n_b, device=db.device)
+        gdb.generate(SEED + 1, 0, n_b)
+        gdb.set_stream(stream.cuda_stream)
+        a16 = np.random.default_rng(31).integers(0, 2**16, size=(31, 12800), dtype=np.uint16)
+        am = np.random.default_rng(32).integers(0, 2**64, size=(31, 200), dtype=np.uint64)
+        g_out = torch.empty((n_b, 31), dtype=torch.int16, device="cuda")
+        for name, fn, n_a, nb in (("dot_u16_31x100000", lambda: iris.dot_u16_batch(a16, gdb, out=g_out), 31, n_b),
+                                  ("dot_bool_31x100000", lambda: iris.dot_bool_batch(am, gdb, out=g_out), 31, n_b)):
+            for _ in range(3):
+                fn()
+            gdb.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                fn()
+            gdb.synchronize()
+            dt = (time.perf_counter() - t0) / 10
+            grid[name] = {"ms_per_grid": dt * 1e3, "elements_per_s": n_a * nb / dt,
+                          "note": "31 host vectors uploaded + prepared per call, rows resident; out = [rows][31] in HBM"}
+        # parity of one column against a plain numpy restatement of src/arch/generic.rs:11-16 on rows read back
+        back = gdb.read_shares(0, 64).astype(np.uint64)
+        want = ((back @ a16.astype(np.uint64).T) & 0xFFFF).astype(np.uint16)
+        iris.dot_u16_batch(a16, gdb, out=g_out)
+        gdb.synchronize()
+        grid["dot_u16_parity_ok"] = bool(np.array_equal(g_out[:64].cpu().numpy().view(np.uint16), want))
+        gdb.close()
+        del g_out
+    except Exception as ex:  # noqa: BLE001
+        grid = {"error": repr(ex)}
+    out["criterion_grids_on_gpu"] = grid
     # the reference's LITERAL signature: batch_process(out, db) with `db` a HOST slice (src/lib.rs:42-52) -- rows are
     # uploaded, re-tiled and scanned in a double-buffered pipeline; PCIe-bound by construction, so the yardstick is a
     # bare pinned host->device copy of the same bytes
