@@ -227,20 +227,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
             const int r0 = (int)(lo < 0 ? 0 : (lo > kTileRows ? kTileRows : lo));
             const int r1 = (int)(hi < 0 ? 0 : (hi > kTileRows ? kTileRows : hi));
             const int64_t tile_off = (trow0 - (int64_t)p.row_begin) * kOutRowBytes;
-#pragma unroll 1
+            // The accumulators fill all 512 TMEM columns, so the next tile's UMMAs cannot start before this tile has
+            // been read out: the read-out is kept as short as possible.  Phase 1 drains the eight queries into
+            // registers, recombining the limbs on the way (two u16 results per register: 128 registers), and releases
+            // tensor memory; phase 2 -- staging the 62-byte rows and the coalesced stores -- then runs under the next
+            // tile's UMMAs.
+            uint32_t packed[kBatchQTile][16];
+#pragma unroll
+            for (int g = 0; g < kBatchQTile; ++g) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                  // 16 columns at a time keeps the live registers down
+                    uint32_t a[16], b[16];
+                    ptx::tmem_ld16(taddr + 32 * g + 16 * h, a);
+                    ptx::tmem_ld16(taddr + 256 + 32 * g + 16 * h, b);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t lo = (a[2 * j] + (b[2 * j] << 8)) & 0xFFFFu;
+                        const uint32_t hi = (a[2 * j + 1] + (b[2 * j + 1] << 8)) << 16;     // slot 31 (padding) is never stored
+                        packed[g][8 * h + j] = lo | hi;
+                    }
+                }
+            }
+            // every accumulator column of this warp's lanes has been read: one arrive per warp lets the leader start
+            // the next tile's UMMAs
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
+#pragma unroll
             for (int g = 0; g < kBatchQTile; ++g) {
                 const uint32_t qi = group * kBatchQTile + g;
-                uint32_t a[32], b[32];
-                ptx::tmem_ld32(taddr + 32 * g, a);
-                ptx::tmem_ld32(taddr + 256 + 32 * g, b);
-                ptx::tmem_wait_ld();
-                if (g == kBatchQTile - 1) {
-                    // every accumulator column of this warp's lanes has been read: one arrive per warp lets the
-                    // leader start the next tile's UMMAs while the last query is still being written out
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
-                }
                 if (qi < p.num_queries) {             // uniform over the CTA
                     uint8_t* outq = reinterpret_cast<uint8_t*>(p.out + (size_t)qi * rows_out * IRIS_ROTATIONS);
                     const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(outq) + tile_off) & 15);
@@ -248,7 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBatchThreads, 1)
                     uint8_t* st = stage_buf + shift + row * kOutRowBytes;
 #pragma unroll
                     for (int j = 0; j < IRIS_ROTATIONS; ++j)
-                        *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)(a[j] + (b[j] << 8));
+                        *reinterpret_cast<uint16_t*>(st + 2 * j) = (uint16_t)(packed[g][j >> 1] >> (16 * (j & 1)));
                     // staging buffers alternate per query: a thread can only write buffer (g&1) again after
                     // passing the barrier of query g+1, which every thread reaches after its copy of query g.
                     ptx::named_bar_sync(1, 128);
