@@ -889,7 +889,8 @@ def multi_gpu_extras(iris, cluster, rank, world, local_rank, ss_rows, c5_rows, t
     out["batched_search_64q_sharded"] = {
         "config": "BASELINE configs[4]" if world > 1 else "BASELINE configs[3] shape at 4 M rows on one GPU",
         "queries": nq, "rows_total": total5, "rows_per_gpu": c5_rows,
-        "note": "16 M rows / N per GPU" + (", capped at 4 M rows per GPU (109 GB): 8 M rows at N = 2" if 16_000_000 // world > c5_rows else ""),
+        "note": (f"16 M rows / {world} = {c5_rows} rows per GPU" if 16_000_000 // world <= c5_rows else
+                 f"capped at 4 M rows per GPU (109 GB of shares + masks): {total5} rows in total at N = {world} instead of 16 M"),
         "ms_per_batch": s5 / bsteps * 1e3, "comparisons_per_s": nq * total5 * bsteps / s5,
         "h2d_bytes_per_step": nq * 3200, "d2h_bytes_per_step": nq * 16,
         "useful_int8_Pops_per_gpu": 2 * c5_rows * nq * 31 * 12800 * 2 / (s5 / bsteps) / 1e15,
