@@ -8,6 +8,8 @@
 //   distances(), denominators()                     src/lib.rs:82-94
 //   decode_distance(&[u16;31], &[u16;31]) -> f64    src/lib.rs:97-107
 //   arch::dot_u16 / arch::dot_bool                  src/arch/generic.rs:4-16
+//   arch::dot_u16_grid / dot_bool_grid              the criterion grids, src/arch/mod.rs:22-72
+//   Cluster                                         the whole mmapped file (src/main.rs:386-400) over several GPUs
 //
 // The reference panics on a length mismatch (assert_eq!, src/lib.rs:43,70); here every failure of the library,
 // including that one, throws iris::Error carrying the status code.  There is no CPU fallback.
@@ -62,6 +64,19 @@ inline uint16_t dot_u16(const std::array<uint16_t, BITS>& a, const std::array<ui
 inline uint16_t dot_bool(const std::array<uint64_t, LIMBS>& a, const std::array<uint64_t, LIMBS>& b, int device = 0) {
     uint16_t out = 0;
     check(iris_dot_bool(device, a.data(), b.data(), &out));
+    return out;
+}
+// The criterion grids (src/arch/mod.rs:22-72): out[i][j] = dot(a[j], b[i]) for every pair, one call.
+inline std::vector<uint16_t> dot_u16_grid(const std::vector<std::array<uint16_t, BITS>>& a,
+                                          const std::vector<std::array<uint16_t, BITS>>& b, int device = 0) {
+    std::vector<uint16_t> out(a.size() * b.size());
+    if (!out.empty()) check(iris_dot_u16_batch(device, a[0].data(), (uint32_t)a.size(), b[0].data(), b.size(), out.data()));
+    return out;
+}
+inline std::vector<uint16_t> dot_bool_grid(const std::vector<std::array<uint64_t, LIMBS>>& a,
+                                           const std::vector<std::array<uint64_t, LIMBS>>& b, int device = 0) {
+    std::vector<uint16_t> out(a.size() * b.size());
+    if (!out.empty()) check(iris_dot_bool_batch(device, a[0].data(), (uint32_t)a.size(), b[0].data(), b.size(), out.data()));
     return out;
 }
 }  // namespace arch
@@ -187,5 +202,54 @@ inline std::pair<double, uint64_t> match_min(const DistanceEngine& de, const Mas
     check(iris_match_min_resident(de.handle(), me.handle(), db.handle(), row_begin, row_end, index_base, &m, &i));
     return {m, i};
 }
+
+
+// One database row-sharded over several GPUs behind one handle (iris_cluster_*): what the participant / coordinator
+// mmap as one file (src/main.rs:386-400, 458-461), with the chunk loops of src/main.rs:425-431, 510-516 run by all GPUs
+// at once and the coordinator's running minimum (src/main.rs:597-621) continued across them.
+class Cluster {
+  public:
+    Cluster(const std::vector<int>& devices, uint64_t capacity_rows, bool shares = true, bool masks = true) {
+        check(iris_cluster_create(devices.data(), (uint32_t)devices.size(), capacity_rows,
+                                  (shares ? IRIS_DB_SHARES : 0u) | (masks ? IRIS_DB_MASKS : 0u), &h_));
+    }
+    ~Cluster() { iris_cluster_destroy(h_); }
+    Cluster(const Cluster&) = delete;
+    Cluster& operator=(const Cluster&) = delete;
+    void load_files(const char* shares_path, const char* masks_path) { check(iris_cluster_load_files(h_, shares_path, masks_path)); }
+    void load(const std::vector<EncodedBits>& shares, const std::vector<Bits>& masks) {
+        check(iris_cluster_load_rows(h_, shares.empty() ? nullptr : shares[0].v.data(), masks.empty() ? nullptr : masks[0].limbs.data(),
+                                     shares.empty() ? masks.size() : shares.size()));
+    }
+    uint64_t len() const {
+        uint64_t a = 0, b = 0;
+        check(iris_cluster_len(h_, nullptr, &a, &b));
+        return a > b ? a : b;
+    }
+    // the participant's request: distances of every row for one template
+    void distances(const Template& t, std::vector<Row31>& out) const {
+        if (out.size() != len()) throw Error(IRIS_ERR_INVALID, "out.len() != db.len()");
+        check(iris_cluster_match_template(h_, t.pattern.limbs.data(), t.mask.limbs.data(), out.empty() ? nullptr : out[0].data(), nullptr));
+    }
+    // the coordinator's side: denominators of every row for one query mask
+    void denominators(const Bits& mask, std::vector<Row31>& out) const {
+        if (out.size() != len()) throw Error(IRIS_ERR_INVALID, "out.len() != db.len()");
+        check(iris_cluster_match(h_, nullptr, mask.limbs.data(), nullptr, out.empty() ? nullptr : out[0].data()));
+    }
+    // whole search for a cluster holding plain encodings: (min distance, row) per template
+    std::vector<std::pair<double, uint64_t>> search(const std::vector<Template>& queries) const {
+        std::vector<double> d(queries.size());
+        std::vector<uint64_t> i(queries.size());
+        if (!queries.empty())
+            check(iris_cluster_search(h_, queries[0].pattern.limbs.data(), (uint32_t)queries.size(), d.data(), i.data()));
+        std::vector<std::pair<double, uint64_t>> out(queries.size());
+        for (std::size_t k = 0; k < queries.size(); ++k) out[k] = {d[k], i[k]};
+        return out;
+    }
+    iris_cluster* handle() const { return h_; }
+
+  private:
+    iris_cluster* h_ = nullptr;
+};
 
 }  // namespace iris

@@ -154,12 +154,60 @@ static void test_engines() {   // src/lib.rs:28-79
     CHECK(best.first == 0.0 && best.second == 1077);
 }
 
+static void test_cluster_and_grids() {
+    // one database over three shards (on as many GPUs as the box has): the participant's and the coordinator's chunk
+    // loops (src/main.rs:425-431, 510-516) and the coordinator's running minimum (src/main.rs:597-621)
+    int gpus = 1;
+    iris::check(iris_device_count(&gpus));
+    const std::size_t n = 777;
+    std::vector<iris::Bits> masks(n);
+    std::vector<iris::EncodedBits> encs(n);
+    std::vector<iris::Template> tmpl(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        tmpl[i] = random_template();
+        masks[i] = tmpl[i].mask;
+        encs[i] = iris::encode(tmpl[i]);
+    }
+    iris::Cluster c({0, 1 % gpus, 2 % gpus}, n);
+    c.load(encs, masks);
+    CHECK(c.len() == n);
+    iris::Template q = tmpl[n - 1];                    // a noisy copy of the last row: it lives in the last shard
+    q.pattern.limbs[3] ^= 0x00FF00FF00FF00FFull;
+    std::vector<iris::Row31> dist(n), den(n), exp(n);
+    c.distances(q, dist);
+    iris::EncodedBits enc = iris::encode(q);
+    for (std::size_t i = 0; i < n; ++i) oracle_distances(enc.v.data(), encs[i].v.data(), exp[i].data());
+    CHECK(dist == exp);
+    c.denominators(q.mask, den);
+    for (std::size_t i = 0; i < n; ++i) oracle_denominators(q.mask.limbs.data(), masks[i].limbs.data(), exp[i].data());
+    CHECK(den == exp);
+    double best = std::numeric_limits<double>::infinity();
+    uint64_t arg = ~0ull;
+    for (std::size_t i = 0; i < n; ++i) {
+        const double d = iris::decode_distance(dist[i], den[i]);
+        if (d < best) best = d, arg = i;
+    }
+    auto r = c.search({q, tmpl[5]});
+    CHECK(r[0].first == best && r[0].second == arg && arg == n - 1);
+    CHECK(r[1].first == 0.0 && r[1].second == 5);
+    // the criterion grids (src/arch/mod.rs:22-72): every pair of independent vectors
+    std::vector<std::array<uint16_t, iris::BITS>> a(5), b(40);
+    for (auto& v : a) v = random_encoded().v;
+    for (auto& v : b) v = random_encoded().v;
+    auto grid = iris::arch::dot_u16_grid(a, b);
+    bool ok = true;
+    for (std::size_t i = 0; i < b.size(); ++i)
+        for (std::size_t j = 0; j < a.size(); ++j) ok &= grid[i * a.size() + j] == oracle_dot_u16(a[j].data(), b[i].data());
+    CHECK(ok);
+}
+
 int main() {
     try {
         test_preprocess();
         test_dotproduct();
         test_encrypted_distances();
         test_engines();
+        test_cluster_and_grids();
     } catch (const iris::Error& e) {
         std::printf("FAIL exception %d: %s\n", e.code, e.what());
         return 2;
