@@ -82,7 +82,8 @@ int iris_db_create(int device, uint64_t capacity_rows, uint32_t flags, iris_db *
 int iris_db_destroy(iris_db *db);
 int iris_db_clear(iris_db *db); /* forget all rows, keep the allocation */
 int iris_db_len(const iris_db *db, uint64_t *n_shares, uint64_t *n_masks);
-/* Append rows given in the reference's flat-file layouts (host pointers). */
+/* Append rows given in the reference's flat-file layouts.  `rows` is host memory; device memory is accepted too, but then
+ * the caller must have synchronised the stream that produced it (the library reads it on the shard's stream). */
 int iris_db_append_shares(iris_db *db, const uint16_t *rows /* [n][12800] */, uint64_t n);
 int iris_db_append_masks(iris_db *db, const uint64_t *rows /* [n][200] */, uint64_t n);
 /* Append rows [first_row, first_row+n_rows) (n_rows = 0: to the end) of a file in the reference's on-disk

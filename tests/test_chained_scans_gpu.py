@@ -85,3 +85,37 @@ def test_reused_output_buffer_keeps_stream_order(ctx):
     db.check_distances_simt(engines[0][0], 0, rows, r0)
     db.check_distances_simt(engines[1][0], 0, rows, r1)
     assert torch.equal(buf[:5_000], r0[:5_000]) and torch.equal(buf[5_000:], r1)
+
+
+def test_engine_freed_and_recreated_while_its_scan_is_still_running():
+    """Device-output scans are asynchronous and engines come from a pool: freeing an engine right behind its scan and
+    building the next one (which takes over the same operand buffers) must not disturb the scan that is still
+    reading them -- the release is ordered on the shard's stream, not on the host."""
+    import torch
+
+    import mpc_iris_code_b200 as iris
+
+    rows = 300_000
+    rng = np.random.default_rng(77)
+    q1, q2 = (rng.integers(0, 2**16, size=12800, dtype=np.uint16) for _ in range(2))
+    m1, m2 = (rng.integers(0, 2**64, size=200, dtype=np.uint64) for _ in range(2))
+    with iris.Database(rows) as db:
+        db.generate(0x1715C0DE, 0, rows)
+        refs = []
+        for q, m in ((q1, m1), (q2, m2)):
+            d = torch.zeros((rows, 31), dtype=torch.int16, device="cuda")
+            n = torch.zeros((rows, 31), dtype=torch.int16, device="cuda")
+            e, me = iris.DistanceEngine(q), iris.MasksEngine(m)
+            iris.match(e, me, db, 0, rows, d, n)
+            db.synchronize()
+            refs.append((d, n))
+        outs = [(torch.zeros_like(refs[0][0]), torch.zeros_like(refs[0][1])) for _ in range(2)]
+        for trial in range(15):
+            for k, (q, m) in enumerate(((q1, m1), (q2, m2))):
+                e, me = iris.DistanceEngine(q), iris.MasksEngine(m)
+                iris.match(e, me, db, 0, rows, outs[k][0], outs[k][1])      # returns while the scan runs
+                e.close()                                                   # freed at once; the next pair reuses the slots
+                me.close()
+            db.synchronize()
+            for k in range(2):
+                assert torch.equal(outs[k][0], refs[k][0]) and torch.equal(outs[k][1], refs[k][1]), (trial, k)
