@@ -253,6 +253,32 @@ def test_cluster_search_ties_go_to_the_lowest_row(iris):
         assert mi[0] == -1 and md[0] == np.inf
 
 
+def test_search_mode_ties_inside_one_cta_go_to_the_lowest_row(iris):
+    # one shard, 313 tiles on 148 CTAs: CTA 0 sees tiles 0, 148 and 296, and lane 5 of its epilogue sees row 5 of each.
+    # The same template at those three rows (and, for good measure, in a neighbouring CTA): the first one must win
+    # (`distance < min_distance`, src/main.rs:617), and when it is removed the next one.
+    n = 40_000
+    rows = [5, 5 + 148 * 128, 5 + 296 * 128, 149 * 128 + 77]
+    tp, tm = synthetic_template(123_456)
+    enc = O.encode(tp, tm)[None, :].copy()
+    q = np.concatenate([tp, tm])[None, :].copy()
+    with iris.Cluster([0], n) as c:
+        c.generate(SEED, n, n_parties=1)
+        db = c.shard(0)[0]
+        for r in rows[1:]:
+            db.write_shares(r, enc)
+            db.write_masks(r, tm[None, :].copy())
+        md, mi = c.search(q)
+        assert (md[0], mi[0]) == (0.0, rows[1])
+        db.write_shares(rows[0], enc)
+        db.write_masks(rows[0], tm[None, :].copy())
+        md, mi = c.search(q)
+        assert (md[0], mi[0]) == (0.0, rows[0])
+        de, me = iris.DistanceEngine.from_template(tp, tm), iris.MasksEngine(tm)
+        assert iris.match_min(de, me, db, 6, n) == (0.0, rows[1])             # a range that starts behind the first copy
+        assert iris.match_min(de, me, db, rows[1] + 1, n, index_base=7) == (0.0, 7 + rows[3])
+
+
 def test_cluster_edge_shapes(iris):
     # fewer rows than shards (empty blocks), an empty database, more queries than one pass holds, zero queries
     with iris.Cluster(cluster_devices(iris, 3), 900) as c:
