@@ -78,6 +78,9 @@ def test_two_million_row_shard_fused_and_batched(iris):
         md, mi = iris.match_min(de, me, db, 0, n, index_base=7_000_000)
         want = iris.combine_min([dd], dn, index_base=7_000_000)
         assert (md, mi) == want
+        # ... and the running minimum continued over ragged blocks of rows (src/main.rs:611-621) gives the same answer
+        parts = [iris.match_min(de, me, db, b, e, index_base=7_000_000) for b, e in ((0, 777_001), (777_001, 1_500_000), (1_500_000, n))]
+        assert min(parts, key=lambda t: (t[0], t[1])) == (md, mi)
         # batched kernels on the last 300 k rows of the shard (tile indices past 2^32 / 32 KiB)
         rb = n - 300_000
         tmpl = np.random.default_rng(64).integers(0, 2**64, size=(3, 400), dtype=np.uint64)
