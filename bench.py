@@ -901,6 +901,28 @@ def multi_gpu_extras(iris, cluster, rank, world, local_rank, ss_rows, c5_rows, t
         "parity_ok": bool(ok)}
     if world == 1:
         return out
+    # -- the full result vectors of all ranks gathered on every rank: scan into the rank's slot, then one grouped
+    # ncclBroadcast per rank over NVLink ("compute, then collective" -- the in-process handle below stores the same
+    # vectors straight into one GPU from the scan epilogues instead)
+    try:
+        rows_g = 1_000_000
+        cluster.generate(SEED, rows_g, first_row_id=rank * rows_g, n_parties=1)
+        cluster.set_index_base(rank * rows_g)
+        p_, m_ = plain_template_of_row(iris, world * rows_g - 1, local_rank)
+        qg = iris.encode(p_, m_, device=local_rank)
+        gd = torch.empty((world * rows_g, 31), dtype=torch.int16, device="cuda")
+        gn = torch.empty((world * rows_g, 31), dtype=torch.int16, device="cuda")
+        sg = timed_host_loop(lambda: cluster.match_allgather(qg, m_, gd, gn), 5, warm=2)
+        mdg, mig = iris.combine_min([gd], gn, device=local_rank)
+        out["full_vectors_allgather"] = {
+            "rows_total": world * rows_g, "ms_per_query": sg / 5 * 1e3, "comparisons_per_s": world * rows_g * 5 / sg,
+            "nvlink_bytes_received_per_gpu": (world - 1) * rows_g * 124,
+            "path": "iris_cluster_match_allgather: fused scan into the rank's slot of two [N_total][31] arrays, then "
+                    "ncclBroadcast of every rank's block (grouped) -- every rank ends up with all vectors",
+            "parity_ok": bool((mdg, mig) == (0.0, world * rows_g - 1))}
+        del gd, gn
+    except Exception as ex:  # noqa: BLE001
+        out["full_vectors_allgather"] = {"error": repr(ex)}
     # -- ONE process, ONE handle, N GPUs: rank 0 drives every GPU of the box through iris_cluster_* (what a Rust host
     # does); the other ranks release their GPUs and wait at a HOST barrier (gloo) so that nothing of theirs runs.
     cluster.close()                                   # every rank frees its shard (and leaves the NCCL communicator)

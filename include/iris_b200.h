@@ -283,6 +283,12 @@ int iris_cluster_search(iris_cluster *c, const uint64_t *templates, uint32_t num
 #define IRIS_UNIQUE_ID_BYTES 128
 int iris_comm_unique_id(void *id_out /* [128] */);
 int iris_cluster_join(iris_cluster *c, const void *unique_id, int rank, int world_size);
+/* Multi-process clusters: iris_cluster_match with the full result vectors of ALL processes gathered on every process
+ * (collective).  The outputs are DEVICE arrays of [rows of all processes][31] u16; process p's rows occupy
+ * [index_base_p, index_base_p + rows_p).  Every process scans into its slot, then the blocks travel over NVLink with one
+ * grouped ncclBroadcast per process.  (Inside one process no second step is needed: see iris_cluster_match.) */
+int iris_cluster_match_allgather(iris_cluster *c, const uint16_t *query, const uint64_t *query_mask,
+                                 uint16_t *distances_out, uint16_t *denominators_out);
 
 /* ---- single-pair wrappers: src/lib.rs:82-87 and :89-94 ---- */
 int iris_distances(int device, const uint16_t query[IRIS_BITS], const uint16_t entry[IRIS_BITS],

@@ -96,6 +96,7 @@ def lib():
         "iris_db_set_overlap": [vp, i32],
         "iris_comm_unique_id": [vp],
         "iris_cluster_join": [vp, vp, i32, i32],
+        "iris_cluster_match_allgather": [vp, vp, vp, vp, vp],
         "iris_db_load_shares_file": [vp, ctypes.c_char_p, u64, u64],
         "iris_db_load_masks_file": [vp, ctypes.c_char_p, u64, u64],
         "iris_db_read_shares": [vp, u64, u64, vp],
@@ -649,6 +650,14 @@ class Cluster:
         _check(lib().iris_cluster_match(self._h, _ptr(query, np.uint16, BITS, "query"), _ptr(query_mask, np.uint64, LIMBS, "query_mask"),
                                         _ptr(distances_out, np.uint16, n, "distances_out"),
                                         _ptr(denominators_out, np.uint16, n, "denominators_out")))
+
+    def match_allgather(self, query=None, query_mask=None, distances_out=None, denominators_out=None) -> None:
+        """Joined (multi-process) clusters: every process scans its rows and all processes end up with the result
+        vectors of ALL rows (device arrays [total rows][31]); collective."""
+        _check(lib().iris_cluster_match_allgather(self._h, _ptr(query, np.uint16, BITS, "query"),
+                                                  _ptr(query_mask, np.uint64, LIMBS, "query_mask"),
+                                                  _ptr(distances_out, np.uint16, 0, "distances_out"),
+                                                  _ptr(denominators_out, np.uint16, 0, "denominators_out")))
 
     def match_template(self, pattern, mask, distances_out, denominators_out=None) -> None:
         n = len(self) * ROTATIONS

@@ -143,6 +143,9 @@ struct Nccl {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     std::string error;
@@ -164,9 +167,13 @@ Nccl* nccl() {
         n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
         n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
         n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(h, "ncclAllGather"));
+        n.Broadcast = reinterpret_cast<decltype(n.Broadcast)>(dlsym(h, "ncclBroadcast"));
+        n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(dlsym(h, "ncclGroupStart"));
+        n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
         n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
         n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-        if (!n.GetUniqueId || !n.CommInitRank || !n.AllGather || !n.CommDestroy || !n.GetErrorString) {
+        if (!n.GetUniqueId || !n.CommInitRank || !n.AllGather || !n.CommDestroy || !n.GetErrorString || !n.Broadcast ||
+            !n.GroupStart || !n.GroupEnd) {
             n.error = "libnccl.so.2 lacks a required symbol";
             n.handle = nullptr;
         }
@@ -194,6 +201,8 @@ struct iris_cluster {
     ResultPair* h_result = nullptr;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    uint64_t* d_layout = nullptr;        // [world][2] = {first global row, rows} of every process, all-gathered per gather
+    uint64_t* h_layout = nullptr;
     std::mutex mu;                       // one operation at a time
     std::vector<std::pair<int, int>> peers;   // (from, to) pairs with peer access enabled
     std::vector<std::pair<int, int>> no_peers;
@@ -297,6 +306,8 @@ extern "C" int iris_cluster_destroy(iris_cluster* c) {
         }
         cudaFree(c->d_merged);
         cudaFree(c->d_all);
+        cudaFree(c->d_layout);
+        if (c->h_layout) cudaFreeHost(c->h_layout);
         if (c->h_result) cudaFreeHost(c->h_result);
     }
     cudaGetLastError();
@@ -706,7 +717,67 @@ extern "C" int iris_cluster_join(iris_cluster* c, const void* unique_id, int ran
         return cfail(IRIS_ERR_CUDA, "ncclCommInitRank failed: %s", n->GetErrorString(r));
     }
     CCK(cudaMalloc(reinterpret_cast<void**>(&c->d_all), (size_t)world_size * kMaxSearchQueries * sizeof(ResultPair)));
+    CCK(cudaMalloc(reinterpret_cast<void**>(&c->d_layout), (size_t)(world_size + 1) * 2 * sizeof(uint64_t)));
+    CCK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_layout), (size_t)(world_size + 1) * 2 * sizeof(uint64_t), cudaHostAllocPortable));
     c->rank = rank;
     c->world = world_size;
+    return IRIS_OK;
+}
+
+// Multi-process clusters: the full per-row result vectors of one query on EVERY process.  Each process scans its rows
+// into its slot of the caller's device array(s) ([rows of all processes][31] u16, slot = index_base .. index_base +
+// local rows) and the blocks are exchanged over NVLink with one grouped ncclBroadcast per process (blocks may differ
+// in size).  Collective: every process calls it with the same kind of query.  This is the "compute, then collective"
+// baseline; inside ONE process the scan epilogues store straight into the destination GPU (iris_cluster_match), which
+// needs no second step.
+extern "C" int iris_cluster_match_allgather(iris_cluster* c, const uint16_t* query, const uint64_t* query_mask,
+                                            uint16_t* distances_out, uint16_t* denominators_out) {
+    if (!c) return cfail(IRIS_ERR_INVALID, "cluster is NULL");
+    if (c->world <= 1 || !c->comm) return cfail(IRIS_ERR_STATE, "the cluster has not joined a multi-process communicator");
+    if ((query && !distances_out) || (query_mask && !denominators_out) || (!query && !query_mask))
+        return cfail(IRIS_ERR_INVALID, "query / output mismatch");
+    for (uint16_t* o : {distances_out, denominators_out}) {
+        cudaPointerAttributes attr;
+        if (o && (cudaPointerGetAttributes(&attr, o) != cudaSuccess || attr.type != cudaMemoryTypeDevice)) {
+            cudaGetLastError();
+            return cfail(IRIS_ERR_INVALID, "the gathered arrays must be device memory");
+        }
+    }
+    Nccl* n = nccl();
+    const uint64_t local = std::max(c->n_shares, c->n_masks);
+    void* rs = nullptr;
+    int rc = iris_db_get_stream(c->shards[0].db, &rs);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(rs);
+    {   // who holds which rows: {index_base, rows} of every process
+        std::lock_guard<std::mutex> lk(c->mu);
+        SetDevice g(c->shards[0].device);
+        c->h_layout[0] = c->index_base;
+        c->h_layout[1] = local;
+        uint64_t* mine = c->d_layout + 2 * (size_t)c->world;
+        CCK(cudaMemcpyAsync(mine, c->h_layout, 16, cudaMemcpyHostToDevice, stream));
+        const ncclResult_t r = n->AllGather(mine, c->d_layout, 2, ncclUint64, c->comm, stream);
+        if (r != ncclSuccess) return cfail(IRIS_ERR_CUDA, "ncclAllGather failed: %s", n->GetErrorString(r));
+        CCK(cudaMemcpyAsync(c->h_layout, c->d_layout, (size_t)c->world * 16, cudaMemcpyDeviceToHost, stream));
+        CCK(cudaStreamSynchronize(stream));
+    }
+    std::vector<uint64_t> layout(c->h_layout, c->h_layout + 2 * (size_t)c->world);
+    // local scan into this process's slot (the shards of this process store at their own offsets inside it)
+    rc = cluster_match(c, query, nullptr, query_mask, query_mask != nullptr,
+                       distances_out ? distances_out + c->index_base * IRIS_ROTATIONS : nullptr,
+                       denominators_out ? denominators_out + c->index_base * IRIS_ROTATIONS : nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SetDevice g(c->shards[0].device);
+    ncclResult_t r = n->GroupStart();
+    for (int p = 0; r == ncclSuccess && p < c->world; ++p) {
+        const size_t off = (size_t)layout[2 * p] * IRIS_ROTATIONS, bytes = (size_t)layout[2 * p + 1] * IRIS_ROTATIONS * sizeof(uint16_t);
+        if (bytes == 0) continue;
+        for (uint16_t* o : {distances_out, denominators_out})
+            if (o && r == ncclSuccess) r = n->Broadcast(o + off, o + off, bytes, ncclUint8, p, c->comm, stream);
+    }
+    if (r == ncclSuccess) r = n->GroupEnd();
+    if (r != ncclSuccess) return cfail(IRIS_ERR_CUDA, "NCCL broadcast of the result blocks failed: %s", n->GetErrorString(r));
+    CCK(cudaStreamSynchronize(stream));
     return IRIS_OK;
 }

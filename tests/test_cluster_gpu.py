@@ -452,6 +452,14 @@ c.set_index_base(b)
 c.join(uid, rank, world)
 md, mi = c.search(tq)
 np.save(sys.argv[6] + f".{{rank}}.npy", np.stack([md, mi.astype(np.float64)]))
+# the full result vectors of all processes, gathered on every process over NCCL
+import torch
+torch.cuda.set_device(rank)
+q = iris.encode(tq[1, :200].copy(), tq[1, 200:].copy(), device=rank)
+dd = torch.zeros((n, 31), dtype=torch.int16, device=f"cuda:{{rank}}")
+dn = torch.zeros((n, 31), dtype=torch.int16, device=f"cuda:{{rank}}")
+c.match_allgather(q, tq[1, 200:].copy(), dd, dn)
+np.save(sys.argv[6] + f".vec{{rank}}.npy", np.stack([dd.cpu().numpy(), dn.cpu().numpy()]))
 c.close()
 """
 
@@ -479,3 +487,8 @@ def test_processes_join_one_cluster_over_nccl(iris, tmp_path):
         c.generate(SEED, n, n_parties=1)
         md, mi = c.search(tq)
         assert np.array_equal(res[0][0], md) and np.array_equal(res[0][1], mi.astype(np.float64))
+        hd, hn = np.zeros((n, 31), np.uint16), np.zeros((n, 31), np.uint16)
+        c.match_template(tq[1, :200].copy(), tq[1, 200:].copy(), hd, hn)
+    for r in range(world):                                       # ... and every process holds every row's vectors
+        vec = np.load(str(tmp_path / "out") + f".vec{r}.npy").view(np.uint16)
+        assert np.array_equal(vec[0], hd) and np.array_equal(vec[1], hn)
