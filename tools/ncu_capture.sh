@@ -17,6 +17,7 @@ cap() {  # name regex skip
 }
 cap scan_fused 'scan_kernel' 1
 cap scan_distances 'scan_kernel' 4
+cap scan_search 'scan_kernel' 7
 cap mask_scan_fp4 'mask_scan_fp4_kernel' 1
 cap batch_distances_s8 'batch_distances_kernel' 1
 cap batch_distances_u8 'batch_distances_kernel' 4

@@ -42,7 +42,12 @@ def main():
     for _ in range(3):
         iris.denominators_batch(mes, db, 0, brows, big)    # mask_scan_fp4_multi_kernel x 16 (four masks per pass)
     db.synchronize()
-    print("min/argmin:", iris.match_min(de, me, db, 0, rows))   # scan + combine_decode + final_min
+    for _ in range(3):
+        best = iris.match_min(de, me, db, 0, rows)          # scan_kernel<1,1,1,search> + final_min_kernel
+    print("min/argmin:", best)
+    iris.match(de, me, db, 0, rows, dist, den)
+    db.synchronize()
+    print("combine:", iris.combine_min([dist], den))        # combine_decode_kernel + final_min_kernel
     print("launches:", iris.launch_count())
 
 
