@@ -26,7 +26,11 @@
  * (the reference calls batch_process from one spawn_blocking thread at a time,
  * src/main.rs:425-431, 510-516); distinct handles may be used from distinct threads.
  * Ownership: the library owns device memory behind the opaque handles; the caller owns
- * every buffer it passes in, and no pointer is retained after a call returns.
+ * every buffer it passes in.  Host inputs (queries, templates, rows) are consumed before the call
+ * returns.  Calls with DEVICE outputs are asynchronous on the shard's stream: the output array must
+ * stay valid until that stream has reached the call (iris_db_synchronize, or the caller's own
+ * stream order after iris_db_set_stream); engines may be freed right away (their operand images
+ * are released in stream order).  Calls with host outputs return when the outputs are complete.
  */
 #ifndef IRIS_B200_H
 #define IRIS_B200_H

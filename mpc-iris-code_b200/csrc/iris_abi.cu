@@ -727,8 +727,8 @@ static int scan_core(iris_db* db, iris_distance_engine* de, iris_masks_engine* m
         p.tile_end = (uint32_t)((row_end + kTileRows - 1) / kTileRows);
         // The reference calls batch_process chunk after chunk (src/main.rs:427-430): consecutive scans on the library's
         // own stream with disjoint outputs may overlap (the next one starts on the SMs the previous one's tail leaves
-        // idle).  After kChain chained launches one ordinary launch drains the chain, so the ranges below are all a
-        // running scan can belong to.  The same holds on a caller-supplied stream: a scan only ever starts early behind
+        // idle).  The ranges below are all a running scan can belong to: after kChain chained launches an ordinary launch
+        // drains the chain, unless every scan of the chain is wide (see below).  The same holds on a caller-supplied stream: a scan only ever starts early behind
         // another scan of this shard (a foreign kernel in between never triggers the programmatic launch, so the scan
         // behind it starts when that kernel has completed); iris_db_set_overlap(db, 0) turns the overlap off.
         const size_t bytes = (size_t)(row_end - row_begin) * kOutRowBytes;
