@@ -240,7 +240,10 @@ int iris_search_batch_resident_async(iris_distance_engine *const *des, iris_mask
  *   - match: every shard's scan kernel stores its [rows][31] result block at its row offset of ONE caller array, which
  *     may live on any GPU of the cluster (peer stores) or in (pinned) host memory (one PCIe link per GPU in parallel);
  *   - several processes (one per GPU, e.g. under torchrun) join one cluster with iris_cluster_join: the merged pairs
- *     of each process are all-gathered over NCCL (libnccl.so.2, loaded at run time) and merged again.
+ *     of each process are all-gathered over NCCL (libnccl.so.2, loaded at run time) and merged again.  The copy used
+ *     is the one the process has already loaded, else the file the environment variable IRIS_NCCL_LIB names, else the
+ *     system's; a process can hold only one libnccl.so.2, so a host that will load a different copy later (Python
+ *     importing torch after its first join) names that copy in IRIS_NCCL_LIB before the first NCCL call.
  * `devices` may name a GPU more than once (several shards on one GPU; used by the tests on one-GPU boxes). ---- */
 typedef struct iris_cluster iris_cluster;
 int iris_cluster_create(const int *devices, uint32_t n_devices, uint64_t capacity_rows, uint32_t flags,

@@ -580,8 +580,29 @@ def cluster_partition(n_total: int, n_shards: int, shard: int):
     return b.value, e.value
 
 
+def _prefer_bundled_nccl() -> None:
+    """A process can hold one libnccl.so.2.  torch links against the copy bundled with it (nvidia-nccl wheel), which is
+    newer than the system's; if the library loaded the system copy first, a later `import torch` would fail with an
+    undefined symbol.  So a Python host points the library (IRIS_NCCL_LIB, read at its first NCCL call) at the
+    bundled copy, without importing torch."""
+    if os.environ.get("IRIS_NCCL_LIB"):
+        return
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        path = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            os.environ["IRIS_NCCL_LIB"] = path
+            return
+
+
 def comm_unique_id() -> bytes:
     """The id rank 0 draws for a multi-process cluster (128 bytes; hand it to the other processes by any channel)."""
+    _prefer_bundled_nccl()
     buf = ctypes.create_string_buffer(128)
     _check(lib().iris_comm_unique_id(buf))
     return buf.raw
@@ -643,6 +664,7 @@ class Cluster:
         _check(lib().iris_cluster_set_index_base(self._h, base))
 
     def join(self, unique_id: bytes, rank: int, world_size: int) -> None:
+        _prefer_bundled_nccl()
         _check(lib().iris_cluster_join(self._h, unique_id, rank, world_size))
 
     def match(self, query=None, query_mask=None, distances_out=None, denominators_out=None) -> None:

@@ -26,7 +26,7 @@ DIAG_LIB_PATH = os.path.join(LIB_DIR, "libiris_b200_diag.so")
 SOURCES = ["iris_kernels.cu", "iris_abi.cu", "iris_batch.cu", "iris_reduce.cu", "iris_maskscan4.cu", "iris_dotbatch.cu",
            "iris_cluster.cu"]
 DIAG_SOURCES = SOURCES + ["iris_maskscan.cu"]
-HEADERS = ["iris_layout.h", "iris_ptx.cuh", "iris_kernels.cuh", "iris_epilogue.cuh", "iris_runtime.cuh",
+HEADERS = ["iris_layout.h", "iris_ptx.cuh", "iris_kernels.cuh", "iris_epilogue.cuh",
            "../../include/iris_b200.h"]
 
 NVCC_FLAGS = [

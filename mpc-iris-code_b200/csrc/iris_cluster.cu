@@ -19,6 +19,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -137,7 +138,9 @@ struct Shard {
     Worker* worker = nullptr;
 };
 
-// ---- NCCL, resolved at run time: the copy the process already has (torch's), else the system's libnccl.so.2
+// ---- NCCL, resolved at run time: the copy the process already has (torch's), else the file IRIS_NCCL_LIB names, else
+// the system's libnccl.so.2.  A process may hold only one library with that soname, so a host that loads another copy
+// LATER (a Python process importing torch after its first join) should name that copy in IRIS_NCCL_LIB up front.
 struct Nccl {
     void* handle = nullptr;
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
@@ -156,6 +159,10 @@ Nccl* nccl() {
     static std::once_flag once;
     std::call_once(once, [] {
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) {
+            const char* path = getenv("IRIS_NCCL_LIB");
+            if (path && *path) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+        }
         if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (!h) {

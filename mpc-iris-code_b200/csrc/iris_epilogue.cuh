@@ -9,7 +9,7 @@ namespace iris {
 // Result stores are streaming stores (st.global.cs): the rows are written once and read much later by another kernel or
 // a copy engine, and plain stores cost the HBM-bound scan 2.4 % (3.91 -> 3.81 ms per 1 M rows fused; tests/diagnostics/
 // store_mode_bench.py).  IRIS_STORE_MODE (compile-time, A/B builds only): 0 = plain st.global, 1 = st.global.cs,
-// 2 = st.global with an L2 evict_first policy (same time as 1).
+// 2 = st.global with an L2 evict_first policy (same time as 1), 3 = st.global with an L2 evict_last policy.
 #ifndef IRIS_STORE_MODE
 #define IRIS_STORE_MODE 1
 #endif
@@ -19,6 +19,11 @@ __device__ __forceinline__ void store_out16(uint8_t* g, const uint4& v) {
 #elif IRIS_STORE_MODE == 2
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+#elif IRIS_STORE_MODE == 3
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
                  : "memory");
 #else

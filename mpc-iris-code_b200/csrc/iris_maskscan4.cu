@@ -95,7 +95,8 @@ constexpr uint32_t kM4DescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 
 // immediate.  The issuing warps' instruction stream is what paces this kernel (tests/diagnostics/umma_bench.cu: a
 // TS-form N = 32 UMMA retires every 16 cycles when issued back to back), hence two of them per tile, each with its
 // own accumulator (the epilogue adds the two partial sums; f32, exact).
-// kFlags (diagnostics): 2 / 4 = timing only, no expansion / no UMMAs (wrong results); 256 = per-role wait profile.
+// kFlags (diagnostics): 2 / 4 = timing only, no expansion / no UMMAs (wrong results); 8 / 16 = wait flavours (A/B);
+// 256 = per-role wait profile.
 constexpr int kP4Stages = 10;                                     // query-operand ring (4 KiB stages) = A-barrier ring
 constexpr int kP4DbStages = 20;                                   // packed-mask ring (2 x 4 KiB stages), covers the HBM latency
 constexpr int kP4ABars = 2 * kM4ARing;
@@ -173,6 +174,20 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     long long prof[3] = {0, 0, 0};
     const long long prof_t0 = kProf ? clock64() : 0;
 #define M4_TIMED(slot, stmt) do { if (kProf) { const long long t_ = clock64(); stmt; prof[slot] += clock64() - t_; } else { stmt; } } while (0)
+#ifdef IRIS_DIAGNOSTICS
+    // A/B (diagnostics build): 8 = the waits off the critical path (producers, epilogue) sleep between polls,
+    // 16 = every wait is a try_wait with a long suspend-time hint
+    // crit: 0 = off the critical path (producers, epilogue), 1 = expanders waiting for packed masks, 2 = expanders
+    // waiting for a TMEM slot, 3 = issuers.  kFlags 16..96: try_wait with a suspend-time hint: 16 = all 2 ms, 32 = all
+    // 100 ns, 48 = all 400 ns, 64 = all 1600 ns, 80 = all but the issuers 400 ns, 96 = only crit 0 and 1 400 ns
+#define M4_WAIT(crit, bar, ph, code) do { \
+        constexpr uint32_t hint_ = kFlags == 16 ? 2000000u : kFlags == 32 ? 100u : kFlags == 64 ? 1600u : 400u; \
+        constexpr bool hinted_ = (kFlags >= 16 && kFlags <= 64) || (kFlags == 80 && (crit) != 3) || (kFlags == 96 && (crit) <= 1); \
+        if (hinted_) ptx::mbar_wait_hint(bar, ph, p.error, code, hint_); \
+        else if (kFlags == 8 && (crit) == 0) ptx::mbar_wait_sleep(bar, ph, p.error, code); else ptx::mbar_wait(bar, ph, p.error, code); } while (0)
+#else
+#define M4_WAIT(crit, bar, ph, code) ptx::mbar_wait(bar, ph, p.error, code)
+#endif
 
     const uint32_t pair_begin = p.tile_begin / kM4Tiles;
     const uint32_t pair_end = (p.tile_end + kM4Tiles - 1) / kM4Tiles;
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step) {
             const uint8_t* mk = p.masks + (size_t)pair * kM4Tiles * kMaskTileBytes;
             for (int c = 0; c < kM4StagesPerTile; ++c) {
-                M4_TIMED(0, ptx::mbar_wait(bars + kEmptyDb + 8 * sd, dph ^ 1u, p.error, kW4Producer));
+                M4_TIMED(0, M4_WAIT(0, bars + kEmptyDb + 8 * sd, dph ^ 1u, kW4Producer));
                 const uint32_t sbase = base + sd * kP4DbStageBytes;
                 const uint32_t fb = bars + kFullDb + 8 * sd;
                 if (ptx::elect_one_sync()) {
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
             for (int rev = 0; rev < kRevsPerTile; ++rev, ph ^= 1u) {
 #pragma unroll
                 for (int s = 0; s < kP4Stages; ++s) {
-                    M4_TIMED(0, ptx::mbar_wait(bars + kEmptyQ + 8 * s, ph ^ 1u, p.error, kW4Producer));
+                    M4_TIMED(0, M4_WAIT(0, bars + kEmptyQ + 8 * s, ph ^ 1u, kW4Producer));
                     const uint32_t fb = bars + kFullQ + 8 * s;
                     if (ptx::elect_one_sync()) {
                         ptx::mbar_arrive_expect_tx(fb, kM4QBytes);
@@ -236,13 +251,13 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
         const uint32_t tfull = bars + kTFull + 8 * t, tempty = bars + kTEmpty + 8 * t;
         uint32_t ph = 0;
         for (uint32_t it = 0; it < my_pairs; ++it) {
-            M4_TIMED(2, ptx::mbar_wait(tempty, (it & 1u) ^ 1u, p.error, kW4MmaTmem));    // accumulator drained
+            M4_TIMED(2, M4_WAIT(3, tempty, (it & 1u) ^ 1u, kW4MmaTmem));    // accumulator drained
             ptx::tc_fence_after();
             for (int rev = 0; rev < kRevsPerTile; ++rev, ph ^= 1u) {
 #pragma unroll
                 for (int u = 0; u < kP4Period; ++u) {            // stage / barrier index j = par + 2u
-                    M4_TIMED(0, ptx::mbar_wait(full0 + 16 * u, ph, p.error, kW4MmaFull));
-                    M4_TIMED(1, ptx::mbar_wait(afull0 + 32 * u, ph, p.error, kW4MmaA));
+                    M4_TIMED(0, M4_WAIT(3, full0 + 16 * u, ph, kW4MmaFull));
+                    M4_TIMED(1, M4_WAIT(3, afull0 + 32 * u, ph, kW4MmaA));
                     ptx::tc_fence_after();
                     const bool low = par ? (u < 2) : (u < 3);    // j = par + 2u < 5; slot j % 5
                     const uint32_t abase = low ? a0 + 2 * u * kM4ASlotCols : a0 + (2 * u - kM4ARing) * kM4ASlotCols;
@@ -273,7 +288,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
         for (uint32_t per = 0; per < my_pairs * kRevsPerTile; ++per, ph ^= 1u) {
 #pragma unroll
             for (int u = 0; u < kP4Period; ++u) {                // stage / barrier index j = set + 2u, slot j % 5
-                M4_TIMED(0, ptx::mbar_wait(bars + kFullDb + 8 * sd, dph, p.error, kW4ExpFull));
+                M4_TIMED(0, M4_WAIT(1, bars + kFullDb + 8 * sd, dph, kW4ExpFull));
                 const uint32_t empty_db = bars + kEmptyDb + 8 * sd;
                 uint32_t v[32];
                 if (!(kFlags & 2)) {
@@ -299,8 +314,8 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
                 // j = set + 2u.  The slot j % 5 was last used by stage g - 5, whose commit went to barrier (j + 5) % 10:
                 // for j < 5 that use belongs to the previous revolution
                 const bool low = set ? (u < 2) : (u < 3);        // j < 5
-                M4_TIMED(1, ptx::mbar_wait(low ? aempty0 + 32 * u + 16 * kM4ARing : aempty0 + 32 * u - 16 * kM4ARing,
-                                           low ? ph ^ 1u : ph, p.error, kW4ExpA));
+                M4_TIMED(1, M4_WAIT(2, low ? aempty0 + 32 * u + 16 * kM4ARing : aempty0 + 32 * u - 16 * kM4ARing,
+                                    low ? ph ^ 1u : ph, kW4ExpA));
                 ptx::tc_fence_after();
                 if (!(kFlags & 2)) {
                     tmem_st32_m4(low ? a0 + 2 * u * kM4ASlotCols : a0 + (2 * u - kM4ARing) * kM4ASlotCols, v);
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
         for (uint32_t pair = pair0; pair < pair_end; pair += pair_step, ++it) {
 #pragma unroll 1
             for (int t = 0; t < kM4Tiles; ++t) {
-                M4_TIMED(0, ptx::mbar_wait(bars + kTFull + 8 * t, it & 1u, p.error, kW4Epilogue));
+                M4_TIMED(0, M4_WAIT(0, bars + kTFull + 8 * t, it & 1u, kW4Epilogue));
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + t * 64u;
                 const int64_t trow0 = ((int64_t)pair * kM4Tiles + t) * kTileRows;
@@ -351,6 +366,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     if (kProf && blockIdx.x == 0 && lane == 0)
         printf("m4prof warp %2d total %lld w0 %lld w1 %lld w2 %lld\n", warp, clock64() - prof_t0, prof[0], prof[1], prof[2]);
 #undef M4_TIMED
+#undef M4_WAIT
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == kM4IssuerWarp0) ptx::tmem_dealloc(tmem_base, kM4TmemCols);
@@ -402,6 +418,13 @@ cudaError_t launch_mask_scan_fp4(const ScanParams& p, int num_sms, cudaStream_t 
         case 2: return launch_m4_t<2>(p, num_sms, stream);
         case 4: return launch_m4_t<4>(p, num_sms, stream);
         case 6: return launch_m4_t<6>(p, num_sms, stream);
+        case 8: return launch_m4_t<8>(p, num_sms, stream);
+        case 16: return launch_m4_t<16>(p, num_sms, stream);
+        case 32: return launch_m4_t<32>(p, num_sms, stream);
+        case 48: return launch_m4_t<48>(p, num_sms, stream);
+        case 64: return launch_m4_t<64>(p, num_sms, stream);
+        case 80: return launch_m4_t<80>(p, num_sms, stream);
+        case 96: return launch_m4_t<96>(p, num_sms, stream);
         case 256: return launch_m4_t<256>(p, num_sms, stream);
         default: break;
     }

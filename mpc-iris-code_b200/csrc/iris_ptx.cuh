@@ -102,6 +102,28 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, i
     }
 }
 
+#ifdef IRIS_DIAGNOSTICS
+// A/B only: try_wait with an explicit suspend-time hint (the hardware parks the warp until the phase completes or the
+// hint expires) instead of the default time limit.
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, int* err, int code, uint32_t hint_ns) {
+    uint64_t t0 = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (ok) return;
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kWatchdogNs) watchdog_fire(err, code);
+    }
+}
+#endif
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // A scan launched with cudaLaunchAttributeProgrammaticStreamSerialization may start its CTAs as soon as every CTA of
 // the previous kernel in the stream has called pdl_launch_dependents() -- i.e. on the SMs that kernel's one-tile tail

@@ -49,9 +49,42 @@ def child(rows: int) -> None:
         db.synchronize()
         best.append(s.elapsed_time(e) / 200)
     ms = min(best)
+    # sustained: 1.5 s back to back with the SM clock and the board power sampled (the kernel follows the clock)
+    import threading
+
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    samples, stop = [], threading.Event()
+
+    def sampler():
+        while not stop.is_set():
+            samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1e3))
+            time.sleep(0.02)
+
+    th = threading.Thread(target=sampler)
+    th.start()
+    t0 = time.time()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    s.record(stream)
+    while time.time() - t0 < 1.5:
+        for _ in range(100):
+            iris.match(None, me, db, 0, rows, None, den)
+        n += 100
+        db.synchronize()
+    e.record(stream)
+    db.synchronize()
+    stop.set()
+    th.join()
+    tail = samples[len(samples) // 2:]
+    mhz = sorted(x[0] for x in tail)[len(tail) // 2]
+    watts = sorted(x[1] for x in tail)[len(tail) // 2]
+    sustained = s.elapsed_time(e) / n
     print(f"variant={os.environ.get('IRIS_M4_VARIANT', '-')}/{os.environ.get('IRIS_MASKSCAN', 'f')} rows={rows} "
           f"parity={'ok' if ok else 'FAIL'} ms={ms:.4f} (runs {' '.join(f'{b:.4f}' for b in best)}) "
-          f"{rows * 1662 / (ms * 1e-3) / 1e9:.0f} GB/s algorithmic", flush=True)
+          f"{rows * 1662 / (ms * 1e-3) / 1e9:.0f} GB/s algorithmic; sustained 1.5 s: {sustained:.4f} ms, {mhz} MHz, {watts:.0f} W",
+          flush=True)
 
 
 def main() -> None:

@@ -205,3 +205,20 @@ def test_rust_build_script_compiles_the_same_sources():
     text = open(os.path.join(ROOT, "integration", "rust", "build.rs")).read()
     listed = re.findall(r'"(iris_[a-z0-9_]+\.cu)"', text)
     assert sorted(listed) == sorted(build.SOURCES)
+
+
+def test_first_nccl_call_does_not_break_a_later_torch_import():
+    """A process holds one libnccl.so.2.  The Python binding points the library at the copy bundled with torch
+    (IRIS_NCCL_LIB) before its first NCCL call, so importing torch AFTERWARDS still resolves the newer symbols
+    torch needs (seen on a two-GPU box: `undefined symbol: ncclDevCommCreate` with the system's older copy)."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import mpc_iris_code_b200 as iris\n"
+            "assert len(iris.comm_unique_id()) == 128\n"
+            "import torch\n"
+            "print('ok', torch.__version__)\n") % ROOT
+    env = {k: v for k, v in os.environ.items() if k != "IRIS_NCCL_LIB"}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
