@@ -818,6 +818,10 @@ def run_b200(args):
             line["extras"] = secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den)
         except Exception as ex:  # noqa: BLE001
             line["extras"] = {"error": repr(ex)}
+        try:
+            line["participant_wire_1q"] = participant_wire(rows)
+        except Exception as ex:  # noqa: BLE001
+            line["participant_wire_1q"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         # the only leg of this arm that touches oracle/: times the CPU port and uses it as the checker for the
         # sampled rows of the GPU result above
@@ -835,6 +839,56 @@ def run_b200(args):
     cluster.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def participant_wire(rows: int, requests: int = 5):
+    """The reference's participant role on the wire (src/main.rs:384-452): bin/iris_participant (C++ over the C ABI) holds a
+    synthetic share database in HBM; a client sends one 3 200-byte Template over loopback TCP and reads rows x 62 bytes
+    back until EOF, as the reference coordinator does (src/main.rs:486-504).  Times are the client's."""
+    import socket
+    import subprocess
+
+    from mpc_iris_code_b200 import build
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    proc = subprocess.Popen([build.PARTICIPANT_PATH, "--synthetic", str(rows), "--bind", f"127.0.0.1:{port}",
+                             "--max-requests", str(requests)], stderr=subprocess.PIPE, text=True)
+    times, firsts = [], []
+    try:
+        while "Listening on" not in proc.stderr.readline():
+            if proc.poll() is not None:
+                raise RuntimeError("iris_participant exited early")
+        template = random_templates(1, 1)[0].tobytes()
+        view = memoryview(bytearray(8 << 20))
+        for _ in range(requests):
+            t0 = time.perf_counter()
+            with socket.create_connection(("127.0.0.1", port)) as c:
+                c.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 8 << 20)
+                c.sendall(template)
+                got, first = 0, None
+                while True:
+                    n = c.recv_into(view)
+                    if n == 0:
+                        break
+                    if first is None:
+                        first = time.perf_counter() - t0
+                    got += n
+            times.append(time.perf_counter() - t0)
+            firsts.append(first)
+            if got != rows * 62:
+                raise RuntimeError(f"short reply: {got} of {rows * 62} bytes")
+        proc.wait(timeout=60)
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    t = sorted(times[1:])[len(times[1:]) // 2]                # the first request warms the connection path up
+    return {"rows": rows, "requests": requests, "ms_per_request": t * 1e3, "best_ms": min(times) * 1e3,
+            "first_byte_ms": sorted(firsts[1:])[len(firsts[1:]) // 2] * 1e3, "comparisons_per_s": rows / t,
+            "wire_GBps": rows * 62 / t / 1e9, "reply_bytes": rows * 62, "batch_rows": 20_000,
+            "note": "request -> EOF seen by a single-connection loopback client (Python recv_into); the scan itself takes "
+                    "~3.7 ms per 1 M rows, the rest is one TCP stream carrying 62 MB (DESIGN.md 6.1)"}
 
 
 def multi_gpu_extras(iris, cluster, rank, world, local_rank, ss_rows, c5_rows, timed_host_loop, host_group):
