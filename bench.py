@@ -641,6 +641,20 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
+    # the search-mode scan (the kernel behind `e2e`) on the SAME uniform shares, for comparison: the scan's time depends a
+    # little on what the database holds (uniform u16 words cost more power than the encodings' {0, 1, 0xFFFF}: DESIGN.md 5.1)
+    pair_u = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        iris.match_min_async(de, me, db, 0, rows, pair_u, index_base=row0)
+    db.synchronize()
+    uev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    uev[0].record(stream)
+    for _ in range(max(3, min(args.steps, 20))):
+        iris.match_min_async(de, me, db, 0, rows, pair_u, index_base=row0)
+    uev[1].record(stream)
+    db.synchronize()
+    search_kernel_ms_uniform = max_over_ranks(uev[0].elapsed_time(uev[1]) / max(3, min(args.steps, 20)))
+
     # ---- the engine API with HOST result buffers (pinned): per step the query and its mask go host->device, both
     # engines are prepared, the shard is scanned, and BOTH result arrays (124 B per row) come back over PCIe.
     q_pin = torch.from_numpy(q.view(np.int16).copy()).pin_memory()
@@ -780,9 +794,12 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3200, "d2h_bytes_per_step": 16, "steps": e2e_steps,
                 "ms_per_query": search_s / e2e_steps * 1e3,
                 "kernel": "scan_kernel<shares,masks,search>: the fused scan with decode_distance + running min/argmin in its "
-                          "epilogue; no per-row results are written, which is why this path can be FASTER than `value` "
-                          "(whose kernel stores 124 B per row)",
+                          "epilogue; no per-row results are written (worth 1.5-2 %), and the database of this leg holds "
+                          "encodings {0, 1, 0xFFFF}, which cost less power than `value`'s uniform u16 shares (another 2-2.5 %: "
+                          "kernel_only_ms_on_uniform_shares is the same kernel over the `value` data) -- which is why this "
+                          "path can be FASTER than `value`",
                 "kernel_only_ms": search_kernel_ms,
+                "kernel_only_ms_on_uniform_shares": search_kernel_ms_uniform,
                 "kernel_roofline": {"achieved_GBps": rows * 27200 / (search_kernel_ms * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": rows * 27200 / (search_kernel_ms * 1e-3) / 1e9 / hbm_peak_gbs()[0],
                                     "algorithmic_bytes_per_launch": rows * 27200},
