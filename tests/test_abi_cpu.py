@@ -222,3 +222,17 @@ def test_first_nccl_call_does_not_break_a_later_torch_import():
     env = {k: v for k, v in os.environ.items() if k != "IRIS_NCCL_LIB"}
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_a_wrong_nccl_path_falls_back_to_the_system_copy():
+    """IRIS_NCCL_LIB only NAMES a copy; a path that cannot be loaded must not disable multi-process clusters."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import mpc_iris_code_b200 as iris\n"
+            "assert len(iris.comm_unique_id()) == 128\n"
+            "print('ok')\n") % ROOT
+    env = dict(os.environ, IRIS_NCCL_LIB="/nonexistent/libnccl.so.2")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
