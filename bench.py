@@ -937,6 +937,27 @@ def multi_gpu_extras(iris, cluster, rank, world, local_rank, ss_rows, c5_rows, t
         "result": list(got["r"]), "expected": [plain_distance(s_p, s_m, t_p, t_m), total - 1],
         "parity_ok": bool(got["r"] == (plain_distance(s_p, s_m, t_p, t_m), total - 1)),
         "path": "iris_cluster_search, 1 query, fixed 4 M-row database split over the ranks (HBM-bound fused scan per shard)"}
+    # -- BASELINE configs[0]'s size (the reference's own CPU-runnable case): 1 query vs 100 000 rows in total -- the
+    # latency floor of a search (engine preparation, launches, the gather, 16 bytes back) rather than a bandwidth figure
+    small = 100_000
+    b0, e0 = iris.cluster_partition(small, world, rank)
+    cluster.generate(SEED, e0 - b0, first_row_id=b0, n_parties=1)
+    cluster.set_index_base(b0)
+    t_p0, t_m0 = plain_template_of_row(iris, small - 1, local_rank)
+    s_p0, s_m0 = noisy_copy(t_p0, t_m0, flips=1350, rotation=5, seed=4)
+    tq0 = np.concatenate([s_p0, s_m0]).reshape(1, 400).copy()
+    got0 = {}
+
+    def step0():
+        md, mi = cluster.search(tq0)
+        got0["r"] = (float(md[0]), int(mi[0]))
+
+    s0 = timed_host_loop(step0, 50, warm=5)
+    exp0 = (plain_distance(s_p0, s_m0, t_p0, t_m0), small - 1)
+    out["search_100k_rows"] = {
+        "rows_total": small, "rows_per_gpu": e0 - b0, "ms_per_query": s0 / 50 * 1e3, "comparisons_per_s": small * 50 / s0,
+        "result": list(got0["r"]), "expected": list(exp0), "parity_ok": bool(got0["r"] == exp0),
+        "path": "iris_cluster_search, 1 query, BASELINE configs[0]'s 100 000 rows split over the ranks (latency floor)"}
     # -- BASELINE configs[4]: 64 queries vs 16 M rows row-sharded (4 M rows = 109 GB per GPU at most)
     nq = 64
     total5 = c5_rows * world
