@@ -871,17 +871,28 @@ def participant_wire(rows: int, requests: int = 5):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     proc = subprocess.Popen([build.PARTICIPANT_PATH, "--synthetic", str(rows), "--bind", f"127.0.0.1:{port}",
-                             "--max-requests", str(requests)], stderr=subprocess.PIPE, text=True)
+                             "--max-requests", str(requests)], stderr=subprocess.PIPE)
     times, firsts = [], []
     try:
-        while "Listening on" not in proc.stderr.readline():
+        import select
+
+        deadline = time.time() + 120.0                       # never let a stuck front-end hang the bench
+        err_fd, err_buf = proc.stderr.fileno(), b""
+        while True:
             if proc.poll() is not None:
                 raise RuntimeError("iris_participant exited early")
+            if time.time() > deadline:
+                raise RuntimeError("iris_participant did not start listening within 120 s")
+            if select.select([err_fd], [], [], 1.0)[0]:
+                err_buf += os.read(err_fd, 4096)
+                if b"Listening on" in err_buf:
+                    break
         template = random_templates(1, 1)[0].tobytes()
         view = memoryview(bytearray(8 << 20))
         for _ in range(requests):
             t0 = time.perf_counter()
-            with socket.create_connection(("127.0.0.1", port)) as c:
+            with socket.create_connection(("127.0.0.1", port), timeout=30.0) as c:
+                c.settimeout(30.0)
                 c.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 8 << 20)
                 c.sendall(template)
                 got, first = 0, None
