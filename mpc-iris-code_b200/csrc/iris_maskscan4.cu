@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
 
     ptx::pdl_launch_dependents();               // the next scan's CTAs may take the SMs this kernel leaves idle
     constexpr bool kProf = (kFlags & 256) != 0;
-    long long prof[3] = {0, 0, 0};
+    long long prof[5] = {0, 0, 0, 0, 0};             // waits 0..2; expanders: 3 = load + expand, 4 = store + hand-over
     const long long prof_t0 = kProf ? clock64() : 0;
 #define M4_TIMED(slot, stmt) do { if (kProf) { const long long t_ = clock64(); stmt; prof[slot] += clock64() - t_; } else { stmt; } } while (0)
 #ifdef IRIS_DIAGNOSTICS
@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
             for (int u = 0; u < kP4Period; ++u) {                // stage / barrier index j = set + 2u, slot j % 5
                 M4_TIMED(0, M4_WAIT(1, bars + kFullDb + 8 * sd, dph, kW4ExpFull));
                 const uint32_t empty_db = bars + kEmptyDb + 8 * sd;
+                const long long sec_a = kProf ? clock64() : 0;
                 uint32_t v[32];
                 if (!(kFlags & 2)) {
                     const uint8_t* pk = pk0 + sd * kP4DbStageBytes;
@@ -314,8 +315,10 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
                 // j = set + 2u.  The slot j % 5 was last used by stage g - 5, whose commit went to barrier (j + 5) % 10:
                 // for j < 5 that use belongs to the previous revolution
                 const bool low = set ? (u < 2) : (u < 3);        // j < 5
+                if (kProf) prof[3] += clock64() - sec_a;
                 M4_TIMED(1, M4_WAIT(2, low ? aempty0 + 32 * u + 16 * kM4ARing : aempty0 + 32 * u - 16 * kM4ARing,
                                     low ? ph ^ 1u : ph, kW4ExpA));
+                const long long sec_b = kProf ? clock64() : 0;
                 ptx::tc_fence_after();
                 if (!(kFlags & 2)) {
                     tmem_st32_m4(low ? a0 + 2 * u * kM4ASlotCols : a0 + (2 * u - kM4ARing) * kM4ASlotCols, v);
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(afull0 + 32 * u);
+                if (kProf) prof[4] += clock64() - sec_b;
             }
         }
     } else {
@@ -364,7 +368,8 @@ __global__ void __launch_bounds__(kP4Threads, 1) mask_scan_fp4_kernel(const Scan
     }
 
     if (kProf && blockIdx.x == 0 && lane == 0)
-        printf("m4prof warp %2d total %lld w0 %lld w1 %lld w2 %lld\n", warp, clock64() - prof_t0, prof[0], prof[1], prof[2]);
+        printf("m4prof warp %2d total %lld w0 %lld w1 %lld w2 %lld load+expand %lld store+handover %lld\n", warp, clock64() - prof_t0,
+               prof[0], prof[1], prof[2], prof[3], prof[4]);
 #undef M4_TIMED
 #undef M4_WAIT
     ptx::tc_fence_before();
