@@ -288,10 +288,23 @@ def secondary_configs(iris, db, stream, rows, de, me, d_dist, d_den):
     m_den = torch.empty((max(sweep_rows), 31), dtype=torch.int16, device="cuda")
     sweep = []
     for n in sweep_rows:
-        ms = _steady_ms(stream, lambda: iris.match(None, me, mdb, 0, n, None, m_den), mdb.synchronize)
+        # consecutive launches scan DIFFERENT n-row windows of the shard (offsets are multiples of a 256-row pair tile),
+        # cycling over all of it: 100 k masks are 160 MB, the size of the L2, and a loop over one window would be
+        # served partly from cache
+        windows = max(1, max(sweep_rows) // n)
+        state = {"i": 0}
+        out_n = m_den[:n]
+
+        def one(n=n, windows=windows, state=state, out_n=out_n):
+            b = (state["i"] % windows) * n // 256 * 256
+            state["i"] += 1
+            iris.match(None, me, mdb, b, b + n, None, out_n)
+
+        ms = _steady_ms(stream, one, mdb.synchronize)
         sweep.append({"rows": n, "ms": ms, "comparisons_per_s": n / (ms * 1e-3),
                       "algorithmic_GBps": n * 1662 / (ms * 1e-3) / 1e9,
-                      "frac_of_hbm_peak": n * 1662 / (ms * 1e-3) / 1e9 / peak, "sm_mhz": _NVML["last_mhz"]})
+                      "frac_of_hbm_peak": n * 1662 / (ms * 1e-3) / 1e9 / peak, "sm_mhz": _NVML["last_mhz"],
+                      "windows": windows})
     mdb.close()
     del m_den
     one_m = next((x for x in sweep if x["rows"] == 1_000_000), sweep[-1])
